@@ -1,0 +1,184 @@
+/* ============================================================================
+ * multih_b200.h — C ABI of libmultih_b200.so: the B200-native (sm_100a) hot path
+ * of Multi-H behind the reference's pipeline surface.
+ *
+ * The reference (danini/multi-h) has no plugin / FFI layer; its boundary is the
+ * C++ class `MultiH` (MultiH/MultiH/MultiH.h:20-149).  Every entry point below
+ * cites the reference member it replaces (paths relative to MultiH/MultiH/).
+ * A C++ shim with the reference's class and method names lives in
+ * include/multih_b200.hpp and forwards to this ABI.
+ *
+ * Conventions
+ *  - plain C: pointers + sizes, no C++/torch types; every call returns an
+ *    mh_status (0 = ok); no exception crosses the boundary; the message of the
+ *    last failure is mh_last_error(ctx).
+ *  - "host" pointers are caller-owned host memory, only touched during the call.
+ *    "d_" pointers are DEVICE pointers on the context's device (from mh_alloc,
+ *    cudaMalloc or a torch tensor's data_ptr()).
+ *  - DEVICE-SPACE data are FP32 and live in the context's normalised image
+ *    coordinates (Hartley-style similarity per image, fixed by mh_set_geometry):
+ *      d_pts  float4[N]   = (x1', y1', x2', y2')
+ *      d_aff  float4[N]   = (a11', a12', a21', a22')  (A' = s2/s1 * A)
+ *      d_hyp  float[K][12]= H' = T2 H T1^-1 row-major (9 used, 3 pad)
+ *    Host-space data are FP64 in pixels exactly as the reference holds them
+ *    (x1 y1 x2 y2 | a11 a12 a21 a22 | 3x3 row-major H, F with x2^T F x1 = 0).
+ *    Thresholds are always given in pixels; the library rescales them.
+ *  - one context = one CUDA device + one stream; a context is not thread-safe,
+ *    distinct contexts are independent.
+ *  - there is NO CPU fallback: without a usable CUDA device mh_create fails with
+ *    MH_ECUDA and nothing else can be called.
+ * ==========================================================================*/
+#ifndef MULTIH_B200_H
+#define MULTIH_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mh_ctx mh_ctx;
+
+typedef enum mh_status {
+  MH_OK = 0,
+  MH_EINVAL = 1,      /* bad argument (null pointer, N < 8 where the reference refuses: MultiH.cpp:44-50, ...) */
+  MH_ECUDA = 2,       /* CUDA runtime / launch failure, or no device */
+  MH_ENCCL = 3,       /* reserved for the multi-GPU layer */
+  MH_EDEGENERATE = 4, /* degenerate geometry (||F|| < 1e-5: MultiH.cpp:779; no cluster left) */
+  MH_ENOMEM = 5
+} mh_status;
+
+/* Mirrors the MultiH constructor (MultiH.h:49-53) and its compile-time constants (MultiH.h:7-18). */
+typedef struct mh_params {
+  double thr_fundamental; /* _thr_fund_mat  (unused on the hot path: F is an input)            */
+  double thr_homography;  /* _thr_hom       threshold_homography, px                           */
+  double locality;        /* _locality      locality_lambda                                    */
+  double lambda;          /* _lambda        spatial coherence weight (energy_lambda)           */
+  int32_t min_inliers;    /* _minimum_inlier_number                                            */
+  double straightness;    /* DEFAULT_LINENESS_THRESHOLD 0.005 (MultiH.h:13)                    */
+  int32_t max_iterations; /* MAX_ITERATION_NUMBER 500 (MultiH.h:14)                            */
+  double convergence;     /* CONVERGENCE_THRESHOLD 1e-5 (MultiH.h:15)                          */
+  int32_t meanshift_metric; /* 0 = L1_REF (MeanShiftClustering.h:76-85), 1 = L2                */
+  uint32_t rng_seed;      /* state of the injected MSVC-rand() restatement (1 = unseeded rand) */
+  int32_t max_gc_cycles;  /* expansion(iter, 1000)  (MultiH.cpp:543)                           */
+} mh_params;
+
+void mh_default_params(mh_params* p); /* main.cpp:55-59: 2.6 / 2.2 / 0.005 / 0.5 / 20 */
+
+/* ---- context ----------------------------------------------------------- */
+mh_status mh_create(const mh_params* params, int device, mh_ctx** out); /* MultiH::MultiH  (MultiH.cpp:10-21) */
+void mh_destroy(mh_ctx* ctx);                                           /* MultiH::~MultiH (MultiH.cpp:23-30) */
+const char* mh_last_error(const mh_ctx* ctx);
+const char* mh_version(void);
+mh_status mh_set_stream(mh_ctx* ctx, void* cuda_stream); /* run on the caller's stream (e.g. torch's current stream) */
+mh_status mh_sync(mh_ctx* ctx);
+mh_status mh_alloc(mh_ctx* ctx, uint64_t bytes, void** d_ptr);
+mh_status mh_free(mh_ctx* ctx, void* d_ptr);
+mh_status mh_host_alloc(mh_ctx* ctx, uint64_t bytes, void** pinned_host_ptr);
+mh_status mh_host_free(mh_ctx* ctx, void* pinned_host_ptr);
+mh_status mh_memcpy_d2h(mh_ctx* ctx, void* host, const void* d_src, uint64_t bytes);
+mh_status mh_memcpy_h2d(mh_ctx* ctx, void* d_dst, const void* host, uint64_t bytes);
+int64_t mh_kernel_launches(const mh_ctx* ctx); /* number of OUR kernels launched by this context so far */
+
+/* ---- pair geometry ------------------------------------------------------
+ * Replaces the members fundamental_matrix / epipole_2 that
+ * GetFundamentalMatrixAndRefineData leaves behind (MultiH.cpp:775-793): F is an
+ * INPUT here.  norm1/norm2 = (scale, tx, ty) of T = [s 0 tx; 0 s ty; 0 0 1] per
+ * image; pass NULL to derive them from a strided sample of `pts_host` (N x 4). */
+mh_status mh_set_geometry(mh_ctx* ctx, const double F[9], const double norm1[3], const double norm2[3],
+                          const double* pts_host, int64_t N);
+mh_status mh_get_geometry(const mh_ctx* ctx, double F[9], double e2[2], double norm1[3], double norm2[3]);
+
+/* ---- host <-> device-space conversion ----------------------------------- */
+/* correspondences in the reference's layout (MultiH.h:78-80) -> normalised float4 arrays */
+mh_status mh_upload_correspondences(mh_ctx* ctx, const double* pts_host, const double* aff_host, int64_t N,
+                                    void* d_pts, void* d_aff /* may be NULL */);
+mh_status mh_hypotheses_from_host(mh_ctx* ctx, const double* H_host /*K x 9 px*/, int32_t K, void* d_hyp);
+mh_status mh_hypotheses_to_host(mh_ctx* ctx, const void* d_hyp, int32_t K, double* H_host /*K x 9 px*/,
+                                int32_t divide_by_h33);
+
+/* ---- K1: per-correspondence HAF hypotheses ------------------------------
+ * MultiH::ComputeLocalHomographies (MultiH.cpp:696-717) -> GetHomographyHAF (:850-911).
+ * precision: 0 = FP32 one-sided Jacobi on the 6x4 system (default), 1 = FP64 A^T A + Jacobi. */
+mh_status mh_haf_hypotheses(mh_ctx* ctx, const void* d_pts, const void* d_aff, int64_t N, void* d_hyp,
+                            int32_t precision);
+
+/* ---- K2: N x K reprojection residual / data cost ------------------------
+ * dataEnergy (MultiH.cpp:473-504) with EnergyDataStruct (MultiH.h:23-47).
+ * dense: int32 (elem_bytes=4) or int16 (2) matrix [N][K+1], site-major, column 0 =
+ * outlier label — the layout GCO's setDataCost(int*) consumes (GCoptimization.h:336-343). */
+mh_status mh_data_cost_dense(mh_ctx* ctx, const void* d_pts, int64_t N, const void* d_hyp, int32_t K, void* d_cost,
+                             int32_t elem_bytes);
+/* raw squared residuals in px^2, float [N][K] (MultiH.cpp:491-498) — parity/debug aid */
+mh_status mh_residuals(mh_ctx* ctx, const void* d_pts, int64_t N, const void* d_hyp, int32_t K, void* d_d2);
+/* fused: nothing N x K touches HBM.  Per site: up to `kmax` (label,cost) entries with d2 < T packed as
+ * (label << 8 | cost) (label 1-based as in the dense matrix; cost 0..255 — requires 100/lambda <= 255), the number of
+ * such entries (may exceed kmax = overflow), and the data-term argmin packed (cost << 32 | label) (label 0 = outlier;
+ * what GCO returns without smoothness, GCoptimization.cpp solveSpecialCases).  Per hypothesis: #sites with d2 < thr_H^2
+ * (the inlier test of MultiH.cpp:441 / :762).  Any output pointer may be NULL.  d_list_count / d_inlier_count /
+ * d_best are (re)initialised by the call. */
+mh_status mh_data_cost_fused(mh_ctx* ctx, const void* d_pts, int64_t N, const void* d_hyp, int32_t K, int32_t kmax,
+                             void* d_list /*u32 [N][kmax]*/, void* d_list_count /*i32 [N]*/,
+                             void* d_best /*u64 [N]*/, void* d_inlier_count /*i32 [K]*/);
+/* MergingStep's inlier scan + straightness statistics (MultiH.cpp:430-463): per hypothesis the inlier count and the
+ * 6 uniques (xx xy x yy y n) of S = sum [x y 1]^T[x y 1] over inliers in PIXEL coordinates (FP64 [K][6]),
+ * and (host side, optional) lambda_min of S and the keep flag (lambda_min >= straightness && count >= 3). */
+mh_status mh_inlier_stats(mh_ctx* ctx, const void* d_pts, int64_t N, const void* d_hyp, int32_t K,
+                          double* scatter_host /*K x 6*/, double* lambda_min_host /*K*/, int32_t* keep_host /*K*/);
+/* ComputeInliersOfHomography (MultiH.cpp:743-768): labels[i] = idx where d2 < thr_H^2 */
+mh_status mh_inliers_of_homography(mh_ctx* ctx, const void* d_pts, int64_t N, const void* d_hyp_one, int32_t idx,
+                                   void* d_labels /*i32 [N]*/);
+
+/* ---- K3: mean-shift -------------------------------------------------------
+ * features: MultiH.cpp:612-646 (10-D, from per-point hypotheses + points) and :359-389 (6-D, from K hypotheses);
+ * output FP64 row-major in PIXEL units exactly as the reference builds them. */
+mh_status mh_features10(mh_ctx* ctx, const void* d_hyp, const void* d_pts, int64_t N, void* d_feat /*f64 [N][10]*/);
+mh_status mh_features6(mh_ctx* ctx, const void* d_hyp, int32_t K, void* d_feat /*f64 [K][6]*/);
+/* MeanShiftClustering<double>::Cluster (MeanShiftClustering.h:22-157): sequential-seed flat-kernel mean-shift, run as ONE
+ * persistent cooperative kernel in FP64 (seeds drawn by the restated MSVC rand()).  d_centres f64 [max_c][D],
+ * d_assign i32 [N] (cluster with most votes, first wins ties).  *C_out = number of centres. */
+mh_status mh_meanshift(mh_ctx* ctx, const void* d_feat, int32_t N, int32_t D, double bandwidth, void* d_centres,
+                       int32_t max_c, void* d_assign, int32_t* C_out, int64_t* stats_out /*[2] or NULL*/);
+
+/* ---- K4: per-label refit ---------------------------------------------------
+ * LabelingStep's gather (MultiH.cpp:545-584) + GetHomographyHAFNonminimal (:913-990, linear solution =
+ * do_numerical_refinement=false).  d_labels i32 [N] in -1..K-1.  Labels without members keep d_hyp[l] untouched
+ * (MultiH.cpp:592-593).  d_count i32 [K] optional. */
+mh_status mh_refit_haf(mh_ctx* ctx, const void* d_pts, const void* d_aff, const void* d_labels, int64_t N, int32_t K,
+                       void* d_hyp, void* d_count);
+/* GetHomography3PT (MultiH.cpp:995-1055, linear solution) per cluster of EstablishStablePointSets (:664-688):
+ * d_assign i32 [N] in -1..C-1; clusters with < 3 members get keep=0 (:667). */
+mh_status mh_refit_3pt(mh_ctx* ctx, const void* d_pts, const void* d_assign, int64_t N, int32_t C, void* d_hyp,
+                       void* d_keep /*i32 [C]*/);
+/* MergingStep's mode -> homography (MultiH.cpp:408-427): 3PT on (0,0),(1,0),(0,1) -> 6-D mode (pixel units). */
+mh_status mh_modes_to_hypotheses(mh_ctx* ctx, const void* d_modes /*f64 [C][6]*/, int32_t C, void* d_hyp);
+
+/* ---- host combinatorial steps (consume GPU-built costs) ------------------- */
+/* Exact 4-D radius neighbourhood replacing FlannBasedMatcher::radiusMatch (MultiH.cpp:231-253). CSR out; call with
+ * adj_host == NULL to size. */
+mh_status mh_neighbourhood(mh_ctx* ctx, const double* pts_host, int32_t N, double radius, int64_t* offsets_host,
+                           int32_t* adj_host, int64_t* total_out);
+/* Alpha-expansion (the role of GCoptimizationGeneralGraph in MultiH.cpp:520-543; own implementation, int64 totals):
+ * dense site-major int32 costs [N][L], Potts weight per DIRECTED adjacency entry. */
+mh_status mh_alpha_expansion(mh_ctx* ctx, const int32_t* cost_host, int32_t N, int32_t L, int32_t potts,
+                             const int64_t* offsets_host, const int32_t* adj_host, const int32_t* init_labels,
+                             int32_t max_cycles, int32_t* labels_out, int64_t* energy_out);
+
+/* ---- whole path ------------------------------------------------------------
+ * MultiH::Process (MultiH.cpp:42-98) from ComputeLocalHomographies on, with F supplied:
+ * K1 -> 10-D mean-shift -> cluster 3PT -> { merge (6-D mean-shift, inlier/straightness test) <-> label (K2 dense costs
+ * -> host alpha-expansion) + refit (K4) } until convergence (MultiH.cpp:224-312).
+ * labels_out: N, -1 = outlier (GetLabels, MultiH.h:62); H_out: up to Kmax x 9 px (GetHomography, MultiH.h:69);
+ * K_out = GetClusterNumber (MultiH.h:67). */
+mh_status mh_process(mh_ctx* ctx, const double* pts_host, const double* aff_host, const double F[9], int32_t N,
+                     int32_t* labels_out, double* H_out, int32_t Kmax, int32_t* K_out);
+double mh_get_energy(const mh_ctx* ctx);        /* GetEnergy          (MultiH.h:74) */
+int32_t mh_get_iterations(const mh_ctx* ctx);   /* GetIterationNumber (MultiH.h:68) */
+/* stage timers mirroring the reference's printf timers (MultiH.cpp:68,74,258,310): ms for
+ * [0] point-wise homographies [1] stable clusters [2] adjacency [3] alternating optimisation [4] total */
+mh_status mh_get_stage_ms(const mh_ctx* ctx, double ms[5]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MULTIH_B200_H */

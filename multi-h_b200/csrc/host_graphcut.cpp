@@ -1,0 +1,315 @@
+// ============================================================================
+// host_graphcut.cpp — host-side combinatorial steps that consume the GPU-built
+// data costs: exact 4-D radius neighbourhood and alpha-expansion.
+//
+// Own implementation (nothing is taken from the reference's vendored GCO /
+// maxflow sources, whose licence forbids redistribution).  It plays the role of
+// GCoptimizationGeneralGraph in MultiH::LabelingStep (MultiH/MultiH/MultiH.cpp:
+// 520-543) and of FlannBasedMatcher::radiusMatch in ClusterMergingAndLabeling
+// (MultiH.cpp:231-253).
+//
+// Equivalence with the reference's optimiser (checked in tests against the
+// reference's GCO compiled in place): GCO's expansion(iter, max) sweeps the
+// labels 0..L-1 in order, accepts a move iff it strictly lowers the energy and
+// stops when a full cycle leaves the energy unchanged (GCoptimization.cpp:
+// 1032-1049, 1212-1289).  Inside a move it labels a site alpha unless the site
+// belongs to the sink tree of the BK search, i.e. unless it can still reach the
+// sink in the residual graph (energy.h get_var -> what_segment(default SOURCE)).
+// That set is a property of the binary energy alone (it is the minimiser with
+// the most alpha labels), so any exact max-flow followed by a reverse
+// reachability pass from the sink reproduces GCO's moves bit for bit.  Totals
+// are int64 (the reference's EnergyType is a 32-bit int, GCoptimization.h:165-170).
+// ============================================================================
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#include "../../include/multih_b200.h"
+
+namespace mh {
+
+// ---------------------------------------------------------------------------
+// Dinic max-flow on a static arc array (paired arcs e, e^1).
+// ---------------------------------------------------------------------------
+class MaxFlow {
+ public:
+  void reset(int n_nodes, size_t arc_hint) {
+    n_ = n_nodes + 2; s_ = n_nodes; t_ = n_nodes + 1;
+    head_.assign(n_, -1);
+    to_.clear(); cap_.clear(); next_.clear();
+    to_.reserve(arc_hint); cap_.reserve(arc_hint); next_.reserve(arc_hint);
+  }
+  void add_edge(int u, int v, int64_t c_uv, int64_t c_vu) {
+    to_.push_back(v); cap_.push_back(c_uv); next_.push_back(head_[u]); head_[u] = (int)to_.size() - 1;
+    to_.push_back(u); cap_.push_back(c_vu); next_.push_back(head_[v]); head_[v] = (int)to_.size() - 1;
+  }
+  // terminal capacities: only the difference needs an arc
+  void add_terminal(int x, int64_t from_source, int64_t to_sink) {
+    if (from_source > to_sink) add_edge(s_, x, from_source - to_sink, 0);
+    else if (to_sink > from_source) add_edge(x, t_, to_sink - from_source, 0);
+  }
+  void solve() {
+    std::vector<int> level(n_), it(n_), queue(n_), stack;
+    std::vector<int> path;  // arcs on the current DFS path
+    for (;;) {
+      std::fill(level.begin(), level.end(), -1);
+      int qh = 0, qt = 0;
+      queue[qt++] = s_; level[s_] = 0;
+      while (qh < qt) {
+        const int u = queue[qh++];
+        for (int e = head_[u]; e >= 0; e = next_[e])
+          if (cap_[e] > 0 && level[to_[e]] < 0) { level[to_[e]] = level[u] + 1; queue[qt++] = to_[e]; }
+      }
+      if (level[t_] < 0) break;
+      for (int i = 0; i < n_; ++i) it[i] = head_[i];
+      // iterative blocking flow
+      path.clear();
+      int u = s_;
+      for (;;) {
+        if (u == t_) {
+          int64_t f = INT64_MAX;
+          for (int e : path) f = std::min(f, cap_[e]);
+          for (int e : path) { cap_[e] -= f; cap_[e ^ 1] += f; }
+          // restart from the first saturated arc
+          size_t k = 0;
+          while (k < path.size() && cap_[path[k]] > 0) ++k;
+          path.resize(k);
+          u = path.empty() ? s_ : to_[path.back()];
+          continue;
+        }
+        int& e = it[u];
+        while (e >= 0 && !(cap_[e] > 0 && level[to_[e]] == level[u] + 1)) e = next_[e];
+        if (e >= 0) { path.push_back(e); u = to_[e]; }
+        else {
+          level[u] = -1;  // dead end
+          if (path.empty()) break;
+          const int back = path.back();
+          path.pop_back();
+          u = to_[back ^ 1];
+        }
+      }
+    }
+    // sink side = nodes that can still reach t in the residual graph
+    reach_t_.assign(n_, 0);
+    std::vector<int>& st = queue;
+    int top = 0;
+    st[top++] = t_; reach_t_[t_] = 1;
+    while (top) {
+      const int v = st[--top];
+      for (int e = head_[v]; e >= 0; e = next_[e]) {
+        const int u = to_[e];  // arc v->u is e, arc u->v is e^1
+        if (!reach_t_[u] && cap_[e ^ 1] > 0) { reach_t_[u] = 1; st[top++] = u; }
+      }
+    }
+  }
+  bool sink_side(int x) const { return reach_t_[x] != 0; }
+
+ private:
+  int n_ = 0, s_ = 0, t_ = 0;
+  std::vector<int> head_, to_, next_;
+  std::vector<int64_t> cap_;
+  std::vector<char> reach_t_;
+};
+
+// symmetric weighted adjacency from the directed CSR the caller hands in: each directed entry (i -> j) stands for one
+// setNeighbors(i, j) call of the reference (MultiH.cpp:532-540), which inserts the pair into BOTH lists.
+struct SymGraph {
+  std::vector<int64_t> off;
+  std::vector<int32_t> nbr;
+  std::vector<int32_t> w;
+};
+
+static void symmetrise(int N, const int64_t* offsets, const int32_t* adj, SymGraph& g) {
+  std::vector<int64_t> deg(N + 1, 0);
+  for (int i = 0; i < N; ++i)
+    for (int64_t e = offsets[i]; e < offsets[i + 1]; ++e) {
+      const int j = adj[e];
+      if (j == i || j < 0 || j >= N) continue;
+      ++deg[i]; ++deg[j];
+    }
+  std::vector<int64_t> start(N + 1, 0);
+  for (int i = 0; i < N; ++i) start[i + 1] = start[i] + deg[i];
+  std::vector<int32_t> tmp(start[N]);
+  std::vector<int64_t> cur(start.begin(), start.end() - 1);
+  for (int i = 0; i < N; ++i)
+    for (int64_t e = offsets[i]; e < offsets[i + 1]; ++e) {
+      const int j = adj[e];
+      if (j == i || j < 0 || j >= N) continue;
+      tmp[cur[i]++] = j; tmp[cur[j]++] = i;
+    }
+  g.off.assign(N + 1, 0);
+  g.nbr.clear(); g.w.clear();
+  g.nbr.reserve(tmp.size()); g.w.reserve(tmp.size());
+  for (int i = 0; i < N; ++i) {
+    std::sort(tmp.begin() + start[i], tmp.begin() + start[i + 1]);
+    for (int64_t k = start[i]; k < start[i + 1];) {
+      int64_t m = k;
+      while (m < start[i + 1] && tmp[m] == tmp[k]) ++m;
+      g.nbr.push_back(tmp[k]); g.w.push_back((int32_t)(m - k));
+      k = m;
+    }
+    g.off[i + 1] = (int64_t)g.nbr.size();
+  }
+}
+
+static int64_t total_energy(const int32_t* cost, int N, int L, int potts, const SymGraph& g, const int32_t* lab) {
+  int64_t e = 0;
+  for (int i = 0; i < N; ++i) {
+    e += cost[(size_t)i * L + lab[i]];
+    for (int64_t k = g.off[i]; k < g.off[i + 1]; ++k) {
+      const int j = g.nbr[k];
+      if (j < i && lab[j] != lab[i]) e += (int64_t)potts * g.w[k];
+    }
+  }
+  return e;
+}
+
+mh_status alpha_expansion(const int32_t* cost, int N, int L, int potts, const int64_t* offsets, const int32_t* adj,
+                          const int32_t* init, int max_cycles, int32_t* lab, int64_t* energy_out) {
+  if (N <= 0 || L < 1) return MH_EINVAL;
+  for (int i = 0; i < N; ++i) {
+    lab[i] = init ? init[i] : 0;
+    if (lab[i] < 0 || lab[i] >= L) return MH_EINVAL;
+  }
+  SymGraph g;
+  static const int64_t zero_off[1] = {0};
+  if (offsets && adj) symmetrise(N, offsets, adj, g);
+  else { g.off.assign(N + 1, 0); (void)zero_off; }
+  const bool have_edges = !g.nbr.empty();
+
+  if (!have_edges) {  // GCO solveSpecialCases: data costs only -> per-site argmin, first label wins ties
+    for (int i = 0; i < N; ++i) {
+      int best = 0;
+      for (int l = 1; l < L; ++l)
+        if (cost[(size_t)i * L + l] < cost[(size_t)i * L + best]) best = l;
+      lab[i] = best;
+    }
+    if (energy_out) *energy_out = total_energy(cost, N, L, potts, g, lab);
+    return MH_OK;
+  }
+
+  std::vector<int> var(N, -1), active;
+  std::vector<int32_t> trial(N);
+  MaxFlow mf;
+  int64_t E = total_energy(cost, N, L, potts, g, lab);
+  if (max_cycles < 0) max_cycles = 1 << 30;
+  for (int cycle = 0; cycle < max_cycles; ++cycle) {
+    const int64_t E_old = E;
+    for (int alpha = 0; alpha < L; ++alpha) {
+      active.clear();
+      for (int i = 0; i < N; ++i)
+        if (lab[i] != alpha) { var[i] = (int)active.size(); active.push_back(i); }
+      if (active.empty()) continue;
+      mf.reset((int)active.size(), (size_t)(g.off[N] + 2 * (int64_t)active.size()));
+      int64_t before = 0;
+      std::vector<int64_t> src(active.size(), 0), snk(active.size(), 0);
+      for (size_t a = 0; a < active.size(); ++a) {
+        const int i = active[a];
+        // x = 0 (source side) takes alpha and pays E0 on the arc to the sink; x = 1 keeps its label
+        snk[a] += cost[(size_t)i * L + alpha];
+        src[a] += cost[(size_t)i * L + lab[i]];
+        before += cost[(size_t)i * L + lab[i]];
+        for (int64_t k = g.off[i]; k < g.off[i + 1]; ++k) {
+          const int j = g.nbr[k];
+          const int64_t w = (int64_t)potts * g.w[k];
+          if (var[j] < 0) {             // neighbour already alpha: pay w iff i keeps its label
+            src[a] += w; before += w;
+          } else if (j < i) {           // both active: E00 = 0, E01 = w, E10 = w, E11 = w*[l_i != l_j]
+            const int b = var[j];
+            const int64_t e11 = lab[i] != lab[j] ? w : 0;
+            before += e11;
+            // E(x_i, x_j) = e11*x_i*x_j-part ... decomposition: pay e11 on i's source arc, then arcs B = w, C = w - e11
+            src[a] += e11;
+            // remaining table: [0, w; w - e11, 0] -> arc i->j (x_i=0,x_j=1) = w, arc j->i (x_j=0, x_i=1) = w - e11
+            mf.add_edge((int)a, b, w, w - e11);
+          }
+        }
+      }
+      for (size_t a = 0; a < active.size(); ++a) mf.add_terminal((int)a, src[a], snk[a]);
+      mf.solve();
+      for (int i = 0; i < N; ++i) trial[i] = lab[i];
+      for (size_t a = 0; a < active.size(); ++a)
+        if (!mf.sink_side((int)a)) trial[active[a]] = alpha;
+      // energy of the same terms under the trial labelling
+      int64_t after = 0;
+      for (size_t a = 0; a < active.size(); ++a) {
+        const int i = active[a];
+        after += cost[(size_t)i * L + trial[i]];
+        for (int64_t k = g.off[i]; k < g.off[i + 1]; ++k) {
+          const int j = g.nbr[k];
+          if (var[j] < 0 || j < i) {
+            if (trial[i] != trial[j]) after += (int64_t)potts * g.w[k];
+          }
+        }
+      }
+      if (after < before) {
+        for (size_t a = 0; a < active.size(); ++a) lab[active[a]] = trial[active[a]];
+        E += after - before;
+      }
+      for (int i : active) var[i] = -1;
+    }
+    if (E == E_old) break;
+  }
+  if (energy_out) *energy_out = total_energy(cost, N, L, potts, g, lab);
+  return MH_OK;
+}
+
+// ---------------------------------------------------------------------------
+// Exact radius neighbourhood on float (x1,y1,x2,y2): d^2 <= radius^2 (OpenCV's
+// FlannBasedMatcher squares maxDistance for the L2 index).  Uniform grid over
+// (x1,y1) with cell = radius.  Neighbours of a site are listed in ascending
+// index order; the site itself is excluded (MultiH.cpp:537).
+// ---------------------------------------------------------------------------
+int64_t radius_neighbourhood(const double* pts, int N, double radius, int64_t* offsets, int32_t* adj) {
+  if (N <= 0) { if (offsets) offsets[0] = 0; return 0; }
+  const float r = (float)radius, r2 = r * r;
+  float minx = 1e30f, miny = 1e30f, maxx = -1e30f, maxy = -1e30f;
+  std::vector<float> p(4 * (size_t)N);
+  for (int i = 0; i < N; ++i) {
+    for (int k = 0; k < 4; ++k) p[4 * (size_t)i + k] = (float)pts[4 * (size_t)i + k];
+    minx = std::min(minx, p[4 * (size_t)i]); maxx = std::max(maxx, p[4 * (size_t)i]);
+    miny = std::min(miny, p[4 * (size_t)i + 1]); maxy = std::max(maxy, p[4 * (size_t)i + 1]);
+  }
+  const float cell = std::max(r, 1e-6f);
+  const int gx = std::max(1, std::min(4096, (int)((maxx - minx) / cell) + 1));
+  const int gy = std::max(1, std::min(4096, (int)((maxy - miny) / cell) + 1));
+  auto cx = [&](float x) { return std::min(gx - 1, std::max(0, (int)((x - minx) / cell))); };
+  auto cy = [&](float y) { return std::min(gy - 1, std::max(0, (int)((y - miny) / cell))); };
+  std::vector<int> cstart((size_t)gx * gy + 1, 0), order(N);
+  for (int i = 0; i < N; ++i) ++cstart[(size_t)cy(p[4 * (size_t)i + 1]) * gx + cx(p[4 * (size_t)i]) + 1];
+  for (size_t c = 0; c < (size_t)gx * gy; ++c) cstart[c + 1] += cstart[c];
+  {
+    std::vector<int> cur(cstart.begin(), cstart.end() - 1);
+    for (int i = 0; i < N; ++i) order[cur[(size_t)cy(p[4 * (size_t)i + 1]) * gx + cx(p[4 * (size_t)i])]++] = i;  // ascending index per cell
+  }
+  int64_t total = 0;
+  std::vector<int32_t> row;
+  for (int i = 0; i < N; ++i) {
+    if (offsets) offsets[i] = total;
+    const float* a = &p[4 * (size_t)i];
+    const int ix = cx(a[0]), iy = cy(a[1]);
+    row.clear();
+    for (int yy = std::max(0, iy - 1); yy <= std::min(gy - 1, iy + 1); ++yy)
+      for (int xx = std::max(0, ix - 1); xx <= std::min(gx - 1, ix + 1); ++xx) {
+        const size_t c = (size_t)yy * gx + xx;
+        for (int k = cstart[c]; k < cstart[c + 1]; ++k) {
+          const int j = order[k];
+          if (j == i) continue;
+          const float* b = &p[4 * (size_t)j];
+          const float d0 = a[0] - b[0], d1 = a[1] - b[1], d2 = a[2] - b[2], d3 = a[3] - b[3];
+          if (d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3 <= r2) row.push_back(j);
+        }
+      }
+    if (adj) {
+      std::sort(row.begin(), row.end());
+      std::memcpy(adj + total, row.data(), sizeof(int32_t) * row.size());
+    }
+    total += (int64_t)row.size();
+  }
+  if (offsets) offsets[N] = total;
+  return total;
+}
+
+}  // namespace mh

@@ -1,0 +1,431 @@
+// ============================================================================
+// K4 — per-label refit (sm_100a).
+//
+// Replaces LabelingStep's serial per-label gather (MultiH/MultiH/MultiH.cpp:545-584)
+// followed by GetHomographyHAFNonminimal (MultiH.cpp:913-990, linear solution)
+// and EstablishStablePointSets' per-cluster GetHomography3PT (MultiH.cpp:664-688,
+// :995-1055 + NormalizePoints, Homography_Refine3PTCallback.h:146-197).
+//
+// Pipeline (all on the context's stream, no host round trip):
+//   1 label histogram   (warp-aggregated atomics)
+//   2 exclusive scan    (one CTA)
+//   3 scatter to CSR    (warp-aggregated cursors) — the device version of the
+//                        reference's gather; also yields the member lists
+//   4 HAF: segmented accumulation of SUM A_i^T A_i (10 uniques, FP64) with a
+//          warp-shuffle segmented scan over the label-sorted order
+//     3PT: one warp per cluster, three passes over its members (centroid, mean
+//          distance, 3x3 normal equations) in FP64
+//   5 batched register-resident eigen-solves (one thread / warp per label)
+// The normal equations are accumulated in PIXEL coordinates in FP64, as the
+// reference does, because the least-squares estimate is not invariant to
+// normalisation (see k1_haf.cu).
+// ============================================================================
+#include "haf_device.cuh"
+
+namespace mh {
+
+// ---- 1..3: labels -> CSR ------------------------------------------------------
+__global__ void label_count_kernel(const int32_t* __restrict__ labels, long long N, int K, int32_t* __restrict__ count) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int l = (i < N) ? labels[i] : -1;
+  const bool ok = l >= 0 && l < K;
+  const unsigned act = __ballot_sync(0xffffffffu, ok);
+  if (!ok) return;
+  const unsigned peers = __match_any_sync(act, l);
+  const int lane = threadIdx.x & 31;
+  if (lane == __ffs(peers) - 1) atomicAdd(count + l, __popc(peers));
+}
+
+// offsets[0..K] = exclusive scan of count[0..K-1]; cursor[l] = offsets[l]
+__global__ void scan_kernel(const int32_t* __restrict__ count, int K, int32_t* __restrict__ offsets,
+                            int32_t* __restrict__ cursor) {
+  __shared__ int32_t warp_sums[32];
+  __shared__ int32_t carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int base = 0; base < K; base += blockDim.x) {
+    const int i = base + threadIdx.x;
+    const int v = (i < K) ? count[i] : 0;
+    int s = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, s, d);
+      if (lane >= d) s += t;
+    }
+    if (lane == 31) warp_sums[warp] = s;
+    __syncthreads();
+    if (warp == 0) {
+      int w = (lane < (int)(blockDim.x >> 5)) ? warp_sums[lane] : 0;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, w, d);
+        if (lane >= d) w += t;
+      }
+      warp_sums[lane] = w;  // inclusive
+    }
+    __syncthreads();
+    const int excl = carry + (warp ? warp_sums[warp - 1] : 0) + s - v;
+    if (i < K) { offsets[i] = excl; cursor[i] = excl; }
+    __syncthreads();
+    if (threadIdx.x == blockDim.x - 1) carry = excl + v;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) offsets[K] = carry;
+}
+
+__global__ void label_scatter_kernel(const int32_t* __restrict__ labels, long long N, int K, int32_t* __restrict__ cursor,
+                                     int32_t* __restrict__ members, int32_t* __restrict__ sorted_label) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int l = (i < N) ? labels[i] : -1;
+  const bool ok = l >= 0 && l < K;
+  const unsigned act = __ballot_sync(0xffffffffu, ok);
+  if (!ok) return;
+  const unsigned peers = __match_any_sync(act, l);
+  const int lane = threadIdx.x & 31, leader = __ffs(peers) - 1;
+  int base = 0;
+  if (lane == leader) base = atomicAdd(cursor + l, __popc(peers));
+  base = __shfl_sync(peers, base, leader);
+  const int pos = base + __popc(peers & ((1u << lane) - 1u));
+  members[pos] = (int32_t)i;
+  if (sorted_label) sorted_label[pos] = l;
+}
+
+// Builds CSR (offsets[K+1], members[M], sorted_label[M]) in ctx->scratch; returns device pointers.
+struct Csr {
+  int32_t* count;
+  int32_t* offsets;
+  int32_t* cursor;
+  int32_t* members;
+  int32_t* sorted_label;
+  double* acc;  // K x 12 doubles, zeroed
+};
+
+static mh_status build_csr(mh_ctx* ctx, const int32_t* d_labels, int64_t N, int K, Csr& c) {
+  const uint64_t kpad = ((uint64_t)K + 64) & ~uint64_t(63);
+  const uint64_t npad = ((uint64_t)N + 64) & ~uint64_t(63);
+  const uint64_t bytes = sizeof(int32_t) * (3 * kpad + 2 * npad) + sizeof(double) * 12 * kpad;
+  MH_TRY(ensure_scratch(ctx, bytes));
+  char* p = (char*)ctx->scratch;
+  c.acc = (double*)p; p += sizeof(double) * 12 * kpad;
+  c.count = (int32_t*)p; p += sizeof(int32_t) * kpad;
+  c.offsets = (int32_t*)p; p += sizeof(int32_t) * kpad;
+  c.cursor = (int32_t*)p; p += sizeof(int32_t) * kpad;
+  c.members = (int32_t*)p; p += sizeof(int32_t) * npad;
+  c.sorted_label = (int32_t*)p;
+  MH_CUDA(ctx, cudaMemsetAsync(c.acc, 0, sizeof(double) * 12 * kpad + sizeof(int32_t) * kpad, ctx->stream));  // acc + count
+  if (N > 0) {
+    label_count_kernel<<<(unsigned)((N + 255) / 256), 256, 0, ctx->stream>>>(d_labels, N, K, c.count);
+    MH_LAUNCHED(ctx, "label_count_kernel");
+  }
+  scan_kernel<<<1, 1024, 0, ctx->stream>>>(c.count, K, c.offsets, c.cursor);
+  MH_LAUNCHED(ctx, "scan_kernel");
+  if (N > 0) {
+    label_scatter_kernel<<<(unsigned)((N + 255) / 256), 256, 0, ctx->stream>>>(d_labels, N, K, c.cursor, c.members,
+                                                                               c.sorted_label);
+    MH_LAUNCHED(ctx, "label_scatter_kernel");
+  }
+  return MH_OK;
+}
+
+// ---- 4a: HAF normal equations, warp-shuffle segmented reduction -----------------
+__global__ void __launch_bounds__(256) haf_segment_accumulate_kernel(const float4* __restrict__ pts,
+                                                                     const float4* __restrict__ aff,
+                                                                     const int32_t* __restrict__ members,
+                                                                     const int32_t* __restrict__ sorted_label,
+                                                                     const int32_t* __restrict__ offsets, int K,
+                                                                     double* __restrict__ acc, HafGeom g) {
+  const int M = offsets[K];
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const bool live = j < M;
+  const int l = live ? sorted_label[j] : -1;
+  double v[10];
+#pragma unroll
+  for (int k = 0; k < 10; ++k) v[k] = 0.0;
+  if (live) {
+    const int i = members[j];
+    const float4 p = pts[i], a = aff[i];
+    const double is1 = 1.0 / g.s1, is2 = 1.0 / g.s2, ra = g.s1 / g.s2;
+    double Mx[4][4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) Mx[r][c] = 0.0;
+    haf_accumulate(((double)p.x - g.t1x) * is1, ((double)p.y - g.t1y) * is1, ((double)p.z - g.t2x) * is2,
+                   ((double)p.w - g.t2y) * is2, a.x * ra, a.y * ra, a.z * ra, a.w * ra, g, Mx);
+    int q = 0;
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int c = r; c < 4; ++c) v[q++] = Mx[r][c];
+  }
+  // segmented inclusive scan over the (sorted) labels of the warp
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int lo = __shfl_up_sync(0xffffffffu, l, d);
+    const bool take = lane >= d && lo == l;
+#pragma unroll
+    for (int k = 0; k < 10; ++k) {
+      const double t = __shfl_up_sync(0xffffffffu, v[k], d);
+      if (take) v[k] += t;
+    }
+  }
+  const int lnext = __shfl_down_sync(0xffffffffu, l, 1);
+  const bool tail = live && (lane == 31 || lnext != l);
+  if (tail) {
+    double* o = acc + 12 * (size_t)l;
+#pragma unroll
+    for (int k = 0; k < 10; ++k) atomicAdd(o + k, v[k]);
+  }
+}
+
+// ---- 5a: batched 4x4 eigen-solves ------------------------------------------------
+__global__ void haf_solve_kernel(const double* __restrict__ acc, const int32_t* __restrict__ count, int K,
+                                 float* __restrict__ hyp, int32_t* __restrict__ count_out, HafGeom g) {
+  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  if (l >= K) return;
+  const int n = count[l];
+  if (count_out) count_out[l] = n;
+  if (n == 0) return;  // MultiH.cpp:592-593: label without members keeps its homography
+  double M[4][4];
+  const double* a = acc + 12 * (size_t)l;
+  int q = 0;
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int c = r; c < 4; ++c) { M[r][c] = a[q]; M[c][r] = a[q]; ++q; }
+  double v[4];
+  smallest_eigvec4(M, v);
+  haf_store(v, g, false, hyp + 12 * (size_t)l);  // no division by h33 (MultiH.cpp:977-989)
+}
+
+mh_status launch_refit_haf(mh_ctx* ctx, const float4* d_pts, const float4* d_aff, const int32_t* d_labels, int64_t N,
+                           int K, float* d_hyp, int32_t* d_count) {
+  if (K <= 0) return MH_OK;
+  if (N > 0x7fffffff) return fail(ctx, MH_EINVAL, "mh_refit_haf: N must fit int32");
+  Csr c;
+  MH_TRY(build_csr(ctx, d_labels, N, K, c));
+  const HafGeom g = haf_geom(ctx);
+  if (N > 0) {
+    haf_segment_accumulate_kernel<<<(unsigned)((N + 255) / 256), 256, 0, ctx->stream>>>(d_pts, d_aff, c.members,
+                                                                                        c.sorted_label, c.offsets, K, c.acc, g);
+    MH_LAUNCHED(ctx, "haf_segment_accumulate_kernel");
+  }
+  haf_solve_kernel<<<(unsigned)((K + 63) / 64), 64, 0, ctx->stream>>>(c.acc, c.count, K, d_hyp, d_count, g);
+  MH_LAUNCHED(ctx, "haf_solve_kernel");
+  return MH_OK;
+}
+
+// ---- 3PT -------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ void mat3_mul_d(const double* A, const double* B, double* C) {
+  double T[9];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) T[i * 3 + j] = A[i * 3] * B[j] + A[i * 3 + 1] * B[3 + j] + A[i * 3 + 2] * B[6 + j];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) C[i] = T[i];
+}
+
+// Everything of GetHomography3PT after the point sums: given the two similarity
+// normalisations (s, mx, my per image) and the 3x3 normal equations, return the
+// pixel-space H.  N (sym 6: 00 01 02 11 12 22) and r (3) are A^T A and A^T b in
+// the per-cluster normalised coordinates.
+struct Norm2 { double s1, mx1, my1, s2, mx2, my2; };
+
+__device__ __forceinline__ void normalised_F_and_epipole(const HafGeom& g, const Norm2& n, double (&Fn)[9], double& ex,
+                                                         double& ey) {
+  // T1^-1 = [1/s 0 mx; 0 1/s my; 0 0 1] for T = [s 0 -mx s; 0 s -my s; 0 0 1]  (3PTcb.h:186-193)
+  const double T1i[9] = {1.0 / n.s1, 0, n.mx1, 0, 1.0 / n.s1, n.my1, 0, 0, 1};
+  const double T2it[9] = {1.0 / n.s2, 0, 0, 0, 1.0 / n.s2, 0, n.mx2, n.my2, 1};
+  mat3_mul_d(T2it, g.F, Fn);
+  mat3_mul_d(Fn, T1i, Fn);  // MultiH.cpp:1009
+  double FFt[3][3], V[3][3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) FFt[i][j] = Fn[i * 3] * Fn[j * 3] + Fn[i * 3 + 1] * Fn[j * 3 + 1] + Fn[i * 3 + 2] * Fn[j * 3 + 2];
+  jacobi_sym<3>(FFt, V);  // MultiH.cpp:1013-1017: eigenvector of the smallest eigenvalue, / z
+  int best = 0;
+  double lo = FFt[0][0];
+#pragma unroll
+  for (int i = 1; i < 3; ++i)
+    if (FFt[i][i] < lo) { lo = FFt[i][i]; best = i; }
+  const double vx = best == 0 ? V[0][0] : best == 1 ? V[0][1] : V[0][2];
+  const double vy = best == 0 ? V[1][0] : best == 1 ? V[1][1] : V[1][2];
+  const double vz = best == 0 ? V[2][0] : best == 1 ? V[2][1] : V[2][2];
+  ex = vx / vz;
+  ey = vy / vz;
+}
+
+// h3 = pinv(A) b through the eigen-decomposition of A^T A: singular values w = sqrt(lambda), dropped when
+// w <= 2*DBL_EPSILON*sum(w) (OpenCV SVBkSb threshold used by Mat::inv(DECOMP_SVD), MultiH.cpp:1038).
+__device__ __forceinline__ void pinv_normal3(const double (&Nq)[6], const double (&r)[3], double (&h)[3]) {
+  double A[3][3] = {{Nq[0], Nq[1], Nq[2]}, {Nq[1], Nq[3], Nq[4]}, {Nq[2], Nq[4], Nq[5]}}, V[3][3];
+  jacobi_sym<3>(A, V);
+  double w[3], sumw = 0;
+#pragma unroll
+  for (int j = 0; j < 3; ++j) { w[j] = sqrt(fmax(A[j][j], 0.0)); sumw += w[j]; }
+  const double thr = 2.0 * 2.220446049250313e-16 * sumw;
+  h[0] = h[1] = h[2] = 0.0;
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    if (w[j] <= thr) continue;
+    const double coef = (V[0][j] * r[0] + V[1][j] * r[1] + V[2][j] * r[2]) / (w[j] * w[j]);
+    h[0] += V[0][j] * coef; h[1] += V[1][j] * coef; h[2] += V[2][j] * coef;
+  }
+}
+
+__device__ __forceinline__ void assemble_3pt_and_store(const double (&h3)[3], const double (&Fn)[9], double ex, double ey,
+                                                       const Norm2& n, const HafGeom& g, float* out) {
+  // MultiH.cpp:1040-1050 (lambda == 1), then H = T2^-1 Hn T1 (MultiH.cpp:1054)
+  double Hn[9];
+  Hn[6] = h3[0]; Hn[7] = h3[1]; Hn[8] = h3[2];
+  Hn[3] = ey * Hn[6] - Fn[0]; Hn[4] = ey * Hn[7] - Fn[1]; Hn[5] = ey * Hn[8] - Fn[2];
+  Hn[0] = ex * Hn[6] + Fn[3]; Hn[1] = ex * Hn[7] + Fn[4]; Hn[2] = ex * Hn[8] + Fn[5];
+  const double T1[9] = {n.s1, 0, -n.mx1 * n.s1, 0, n.s1, -n.my1 * n.s1, 0, 0, 1};
+  const double T2i[9] = {1.0 / n.s2, 0, n.mx2, 0, 1.0 / n.s2, n.my2, 0, 0, 1};
+  double H[9];
+  mat3_mul_d(T2i, Hn, H);
+  mat3_mul_d(H, T1, H);
+  // pixel H -> context-normalised FP32 (free scale): H' = Tc2 H Tc1^-1
+  const double C2[9] = {g.s2, 0, g.t2x, 0, g.s2, g.t2y, 0, 0, 1};
+  const double C1i[9] = {1.0 / g.s1, 0, -g.t1x / g.s1, 0, 1.0 / g.s1, -g.t1y / g.s1, 0, 0, 1};
+  mat3_mul_d(C2, H, H);
+  mat3_mul_d(H, C1i, H);
+  double m = 0.0;
+#pragma unroll
+  for (int k = 0; k < 9; ++k) m = fmax(m, fabs(H[k]));
+  const double sc = m > 0.0 ? 1.0 / m : 1.0;
+  float4* o = reinterpret_cast<float4*>(out);
+  o[0] = make_float4((float)(H[0] * sc), (float)(H[1] * sc), (float)(H[2] * sc), (float)(H[3] * sc));
+  o[1] = make_float4((float)(H[4] * sc), (float)(H[5] * sc), (float)(H[6] * sc), (float)(H[7] * sc));
+  o[2] = make_float4((float)(H[8] * sc), 0.f, 0.f, 0.f);
+}
+
+// accumulate the two 3PT rows of one normalised pair (MultiH.cpp:1026-1035)
+__device__ __forceinline__ void rows_3pt(double x1, double y1, double x2, double y2, double ex, double ey,
+                                         const double (&Fn)[9], double (&Nq)[6], double (&r)[3]) {
+  const double a0 = ex * x1 - x2 * x1, a1 = ex * y1 - x2 * y1, a2 = ex - x2;
+  const double b0 = ey * x1 - y2 * x1, b1 = ey * y1 - y2 * y1, b2 = ey - y2;
+  const double ra = -(x1 * Fn[3] + y1 * Fn[4] + Fn[5]);
+  const double rb = (x1 * Fn[0] + y1 * Fn[1] + Fn[2]);
+  Nq[0] += a0 * a0 + b0 * b0; Nq[1] += a0 * a1 + b0 * b1; Nq[2] += a0 * a2 + b0 * b2;
+  Nq[3] += a1 * a1 + b1 * b1; Nq[4] += a1 * a2 + b1 * b2; Nq[5] += a2 * a2 + b2 * b2;
+  r[0] += a0 * ra + b0 * rb; r[1] += a1 * ra + b1 * rb; r[2] += a2 * ra + b2 * rb;
+}
+
+// one warp per cluster
+__global__ void __launch_bounds__(128) cluster_3pt_kernel(const float4* __restrict__ pts,
+                                                          const int32_t* __restrict__ members,
+                                                          const int32_t* __restrict__ offsets, int C,
+                                                          float* __restrict__ hyp, int32_t* __restrict__ keep, HafGeom g) {
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (c >= C) return;
+  const int beg = offsets[c], end = offsets[c + 1], n = end - beg;
+  if (n < 3) {  // MultiH.cpp:667
+    if (lane == 0) keep[c] = 0;
+    return;
+  }
+  const double is1 = 1.0 / g.s1, is2 = 1.0 / g.s2;
+  // pass 1: centroids (3PTcb.h:166-168)
+  double sx1 = 0, sy1 = 0, sx2 = 0, sy2 = 0;
+  for (int j = beg + lane; j < end; j += 32) {
+    const float4 p = pts[members[j]];
+    sx1 += ((double)p.x - g.t1x) * is1; sy1 += ((double)p.y - g.t1y) * is1;
+    sx2 += ((double)p.z - g.t2x) * is2; sy2 += ((double)p.w - g.t2y) * is2;
+  }
+  Norm2 nm;
+  nm.mx1 = warp_sum(sx1) / n; nm.my1 = warp_sum(sy1) / n; nm.mx2 = warp_sum(sx2) / n; nm.my2 = warp_sum(sy2) / n;
+  // pass 2: mean distance to the centroid (3PTcb.h:171-179)
+  double d1 = 0, d2 = 0;
+  for (int j = beg + lane; j < end; j += 32) {
+    const float4 p = pts[members[j]];
+    const double x1 = ((double)p.x - g.t1x) * is1 - nm.mx1, y1 = ((double)p.y - g.t1y) * is1 - nm.my1;
+    const double x2 = ((double)p.z - g.t2x) * is2 - nm.mx2, y2 = ((double)p.w - g.t2y) * is2 - nm.my2;
+    d1 += sqrt(x1 * x1 + y1 * y1);
+    d2 += sqrt(x2 * x2 + y2 * y2);
+  }
+  nm.s1 = sqrt(2.0) / (warp_sum(d1) / n);
+  nm.s2 = sqrt(2.0) / (warp_sum(d2) / n);
+  double Fn[9], ex, ey;
+  normalised_F_and_epipole(g, nm, Fn, ex, ey);
+  // pass 3: normal equations
+  double Nq[6] = {0, 0, 0, 0, 0, 0}, r[3] = {0, 0, 0};
+  for (int j = beg + lane; j < end; j += 32) {
+    const float4 p = pts[members[j]];
+    const double x1 = (((double)p.x - g.t1x) * is1 - nm.mx1) * nm.s1, y1 = (((double)p.y - g.t1y) * is1 - nm.my1) * nm.s1;
+    const double x2 = (((double)p.z - g.t2x) * is2 - nm.mx2) * nm.s2, y2 = (((double)p.w - g.t2y) * is2 - nm.my2) * nm.s2;
+    rows_3pt(x1, y1, x2, y2, ex, ey, Fn, Nq, r);
+  }
+#pragma unroll
+  for (int k = 0; k < 6; ++k) Nq[k] = warp_sum(Nq[k]);
+#pragma unroll
+  for (int k = 0; k < 3; ++k) r[k] = warp_sum(r[k]);
+  if (lane == 0) {
+    double h3[3];
+    pinv_normal3(Nq, r, h3);
+    assemble_3pt_and_store(h3, Fn, ex, ey, nm, g, hyp + 12 * (size_t)c);
+    keep[c] = 1;
+  }
+}
+
+mh_status launch_refit_3pt(mh_ctx* ctx, const float4* d_pts, const int32_t* d_assign, int64_t N, int C, float* d_hyp,
+                           int32_t* d_keep) {
+  if (C <= 0) return MH_OK;
+  if (N > 0x7fffffff) return fail(ctx, MH_EINVAL, "mh_refit_3pt: N must fit int32");
+  Csr c;
+  MH_TRY(build_csr(ctx, d_assign, N, C, c));
+  const unsigned blocks = (unsigned)(((uint64_t)C * 32 + 127) / 128);
+  cluster_3pt_kernel<<<blocks, 128, 0, ctx->stream>>>(d_pts, c.members, c.offsets, C, d_hyp, d_keep, haf_geom(ctx));
+  MH_LAUNCHED(ctx, "cluster_3pt_kernel");
+  return MH_OK;
+}
+
+// MergingStep: mode (6-D feature, pixel units) -> homography by 3PT on (0,0),(1,0),(0,1) (MultiH.cpp:408-427).
+__global__ void modes_to_hyp_kernel(const double* __restrict__ modes, int C, float* __restrict__ hyp, HafGeom g) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double* m = modes + 6 * (size_t)c;
+  const double p1[3][2] = {{0, 0}, {1, 0}, {0, 1}};
+  const double p2[3][2] = {{m[0], m[1]}, {m[2], m[3]}, {m[4], m[5]}};
+  Norm2 nm;
+  nm.mx1 = 1.0 / 3.0; nm.my1 = 1.0 / 3.0;
+  nm.mx2 = (p2[0][0] + p2[1][0] + p2[2][0]) * (1.0 / 3.0);
+  nm.my2 = (p2[0][1] + p2[1][1] + p2[2][1]) * (1.0 / 3.0);
+  double d1 = 0, d2 = 0;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    d1 += sqrt((p1[i][0] - nm.mx1) * (p1[i][0] - nm.mx1) + (p1[i][1] - nm.my1) * (p1[i][1] - nm.my1));
+    d2 += sqrt((p2[i][0] - nm.mx2) * (p2[i][0] - nm.mx2) + (p2[i][1] - nm.my2) * (p2[i][1] - nm.my2));
+  }
+  nm.s1 = sqrt(2.0) / (d1 / 3.0);
+  nm.s2 = sqrt(2.0) / (d2 / 3.0);
+  double Fn[9], ex, ey;
+  normalised_F_and_epipole(g, nm, Fn, ex, ey);
+  double Nq[6] = {0, 0, 0, 0, 0, 0}, r[3] = {0, 0, 0};
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+    rows_3pt((p1[i][0] - nm.mx1) * nm.s1, (p1[i][1] - nm.my1) * nm.s1, (p2[i][0] - nm.mx2) * nm.s2,
+             (p2[i][1] - nm.my2) * nm.s2, ex, ey, Fn, Nq, r);
+  double h3[3];
+  pinv_normal3(Nq, r, h3);
+  assemble_3pt_and_store(h3, Fn, ex, ey, nm, g, hyp + 12 * (size_t)c);
+}
+
+mh_status launch_modes_to_hyp(mh_ctx* ctx, const double* d_modes, int C, float* d_hyp) {
+  if (C <= 0) return MH_OK;
+  modes_to_hyp_kernel<<<(unsigned)((C + 63) / 64), 64, 0, ctx->stream>>>(d_modes, C, d_hyp, haf_geom(ctx));
+  MH_LAUNCHED(ctx, "modes_to_hyp_kernel");
+  return MH_OK;
+}
+
+}  // namespace mh

@@ -1,0 +1,665 @@
+// ============================================================================
+// multih_oracle.cpp — CPU FP64 restatement of Multi-H's data-parallel hot path.
+//
+// THIS IS TEST INFRASTRUCTURE, NOT PRODUCT CODE.  Only tests/, the smoke check
+// in __graft_entry__.py and bench.py's cpu_baseline / --impl reference legs may
+// load it.  The product (libmultih_b200.so) never links, calls or falls back
+// to anything in this directory.
+//
+// It restates, OpenCV-free and in double precision, the reference functions
+// listed in SURVEY.md §8(a); every function cites the reference file:line it
+// follows (paths relative to /root/reference/MultiH/MultiH/).
+//
+// Parity status: the reference (MSVC + PPL + OpenCV 3.1.0) cannot be built or
+// run here, and it ships no unit tests or per-function golden vectors.  The
+// restatement is therefore pinned by (1) tests/golden/*.npz, produced by
+// tests/golden/make_golden.py — an independent line-by-line transliteration of
+// the same reference functions on top of the real OpenCV numerical routines
+// (cv2.eigen, cv2.invert(DECOMP_SVD), cv2 4.13; the reference pins 3.1.0),
+// (2) analytic known-answer tests (noise-free plane => generating H),
+// (3) the integer cost constants 4901 / 9802 / 0..200 at default parameters,
+// (4) the reference's own alpha-expansion compiled in place (oracle/_ref) and
+// (5) the coarse structure of Executable/results/barrsmith.  Per-point labels of
+// the shipped multih.exe are NOT reproducible => "parity
+// pinned on restated functions, unpinned on the end-to-end labelling".
+//
+// Third-party arithmetic restated here (absent from /root/reference): OpenCV
+// 3.1.0 cv::eigen on symmetric input (Jacobi; eigenvalues descending,
+// eigenvectors in rows), cv::Mat::inv(DECOMP_SVD) (Jacobi SVD + backSubst with
+// threshold 2*DBL_EPSILON*sum(w)), cv::Mat::inv() on 3x3.
+// ============================================================================
+#include <algorithm>
+#include <atomic>
+#include <cfloat>
+#include <cmath>
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+#include <thread>
+#include <vector>
+
+namespace {
+
+// ---------------------------------------------------------------------------
+// cv::eigen restatement for symmetric n x n (n <= 8): cyclic Jacobi, then sort
+// eigenvalues descending, eigenvectors returned in ROWS (MH.cpp:893-895 takes
+// EVec.row(3) == smallest eigenvalue).
+// ---------------------------------------------------------------------------
+void sym_eigen(int n, const double* Ain, double* evals, double* evecs_rows) {
+  double A[64], V[64];
+  for (int i = 0; i < n * n; ++i) A[i] = Ain[i];
+  for (int i = 0; i < n; ++i)
+    for (int j = 0; j < n; ++j) V[i * n + j] = (i == j) ? 1.0 : 0.0;
+  for (int sweep = 0; sweep < 64; ++sweep) {
+    double off = 0.0, diag = 0.0;
+    for (int i = 0; i < n; ++i) {
+      diag += A[i * n + i] * A[i * n + i];
+      for (int j = i + 1; j < n; ++j) off += A[i * n + j] * A[i * n + j];
+    }
+    if (off <= 1e-300 || off <= 1e-34 * diag) break;
+    for (int p = 0; p < n - 1; ++p)
+      for (int q = p + 1; q < n; ++q) {
+        double apq = A[p * n + q];
+        if (apq == 0.0) continue;
+        double app = A[p * n + p], aqq = A[q * n + q];
+        double theta = (aqq - app) / (2.0 * apq);
+        double t = (theta >= 0 ? 1.0 : -1.0) / (std::fabs(theta) + std::sqrt(theta * theta + 1.0));
+        double c = 1.0 / std::sqrt(t * t + 1.0), s = t * c;
+        for (int k = 0; k < n; ++k) {  // A <- A J
+          double akp = A[k * n + p], akq = A[k * n + q];
+          A[k * n + p] = c * akp - s * akq;
+          A[k * n + q] = s * akp + c * akq;
+        }
+        for (int k = 0; k < n; ++k) {  // A <- J^T A
+          double apk = A[p * n + k], aqk = A[q * n + k];
+          A[p * n + k] = c * apk - s * aqk;
+          A[q * n + k] = s * apk + c * aqk;
+        }
+        for (int k = 0; k < n; ++k) {  // V <- V J (columns are eigenvectors)
+          double vkp = V[k * n + p], vkq = V[k * n + q];
+          V[k * n + p] = c * vkp - s * vkq;
+          V[k * n + q] = s * vkp + c * vkq;
+        }
+      }
+  }
+  int order[8];
+  for (int i = 0; i < n; ++i) order[i] = i;
+  std::sort(order, order + n, [&](int a, int b) { return A[a * n + a] > A[b * n + b]; });
+  for (int r = 0; r < n; ++r) {
+    int c = order[r];
+    evals[r] = A[c * n + c];
+    for (int k = 0; k < n; ++k) evecs_rows[r * n + k] = V[k * n + c];
+  }
+}
+
+void mat3_mul(const double* A, const double* B, double* C) {
+  double T[9];
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) T[i * 3 + j] = A[i * 3] * B[j] + A[i * 3 + 1] * B[3 + j] + A[i * 3 + 2] * B[6 + j];
+  std::memcpy(C, T, sizeof(T));
+}
+
+// Epipole in image 2: last row of eigen(F F^T), divided by z (MH.cpp:789-793;
+// same construction on the normalised F at MH.cpp:1013-1017).
+void epipole2(const double* F, double* e /*3*/) {
+  double FFt[9];
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) FFt[i * 3 + j] = F[i * 3] * F[j * 3] + F[i * 3 + 1] * F[j * 3 + 1] + F[i * 3 + 2] * F[j * 3 + 2];
+  double ev[3], evec[9];
+  sym_eigen(3, FFt, ev, evec);
+  e[0] = evec[6] / evec[8];
+  e[1] = evec[7] / evec[8];
+  e[2] = 1.0;
+}
+
+// The six HAF rows of one affine correspondence (MH.cpp:859-887 == :938-966).
+inline void haf_rows(const double* p /*x1 y1 x2 y2*/, const double* a /*a11 a12 a21 a22*/, const double* F, double ex,
+                     double ey, double R[6][4]) {
+  const double x1 = p[0], y1 = p[1], x2 = p[2], y2 = p[3];
+  const double a11 = a[0], a12 = a[1], a21 = a[2], a22 = a[3];
+  R[0][0] = a11 * x1 + x2 - ex; R[0][1] = a11 * y1;           R[0][2] = a11; R[0][3] = -F[3];
+  R[1][0] = a12 * x1;           R[1][1] = a12 * y1 + x2 - ex; R[1][2] = a12; R[1][3] = -F[4];
+  R[2][0] = a21 * x1 + y2 - ey; R[2][1] = a21 * y1;           R[2][2] = a21; R[2][3] = F[0];
+  R[3][0] = a22 * x1;           R[3][1] = a22 * y1 + y2 - ey; R[3][2] = a22; R[3][3] = F[1];
+  R[4][0] = ex * x1 - x2 * x1;  R[4][1] = ex * y1 - x2 * y1;  R[4][2] = ex - x2;
+  R[4][3] = x1 * F[3] + y1 * F[4] + F[5];
+  R[5][0] = ey * x1 - y2 * x1;  R[5][1] = ey * y1 - y2 * y1;  R[5][2] = ey - y2;
+  R[5][3] = -(x1 * F[0] + y1 * F[1] + F[2]);
+}
+
+// H from v = (h31,h32,h33,lambda) (MH.cpp:899-909 == :979-989).
+inline void haf_assemble(const double* v, const double* F, double ex, double ey, double* H) {
+  H[6] = v[0]; H[7] = v[1]; H[8] = v[2];
+  const double lam = v[3];
+  H[3] = ey * H[6] - lam * F[0];
+  H[4] = ey * H[7] - lam * F[1];
+  H[5] = ey * H[8] - lam * F[2];
+  H[0] = ex * H[6] + lam * F[3];
+  H[1] = ex * H[7] + lam * F[4];
+  H[2] = ex * H[8] + lam * F[5];
+}
+
+void parallel_for(int64_t n, int threads, const std::function<void(int64_t, int64_t)>& body) {
+  if (threads <= 1 || n < 2) { body(0, n); return; }
+  std::vector<std::thread> pool;
+  int64_t chunk = (n + threads - 1) / threads;
+  for (int t = 0; t < threads; ++t) {
+    int64_t b = t * chunk, e = std::min<int64_t>(n, b + chunk);
+    if (b >= e) break;
+    pool.emplace_back([=, &body] { body(b, e); });
+  }
+  for (auto& th : pool) th.join();
+}
+
+// C round(): half away from zero, then int conversion (MH.cpp:479,502,503,510).
+inline int c_round(double v) { return (int)std::round(v); }
+
+// Hartley normalisation of n 2-D points (3PTcb.h:161-195, CV_64F branch):
+// centroid -> 0, mean distance -> sqrt(2);  T = [s 0 -mx*s; 0 s -my*s; 0 0 1].
+void normalize_points(const double* pts, int n, double* out, double* T) {
+  double mx = 0, my = 0;
+  for (int i = 0; i < n; ++i) { mx += pts[2 * i]; my += pts[2 * i + 1]; }
+  mx *= 1.0 / n; my *= 1.0 / n;
+  double avg = 0;
+  for (int i = 0; i < n; ++i) {
+    out[2 * i] = pts[2 * i] - mx; out[2 * i + 1] = pts[2 * i + 1] - my;
+    avg += std::sqrt(out[2 * i] * out[2 * i] + out[2 * i + 1] * out[2 * i + 1]);
+  }
+  avg /= n;
+  const double ratio = std::sqrt(2.0) / avg;
+  for (int i = 0; i < 2 * n; ++i) out[i] *= ratio;
+  T[0] = ratio; T[1] = 0; T[2] = -mx * ratio;
+  T[3] = 0; T[4] = ratio; T[5] = -my * ratio;
+  T[6] = 0; T[7] = 0; T[8] = 1;
+}
+
+// inverse of the similarity T above (exact; cv::Mat::inv() on 3x3, MH.cpp:1009,1054)
+void inv_similarity(const double* T, double* Ti) {
+  const double s = T[0];
+  Ti[0] = 1.0 / s; Ti[1] = 0; Ti[2] = -T[2] / s;
+  Ti[3] = 0; Ti[4] = 1.0 / s; Ti[5] = -T[5] / s;
+  Ti[6] = 0; Ti[7] = 0; Ti[8] = 1;
+}
+
+// x = pinv(A) b for A (m x 3), as cv::Mat::inv(DECOMP_SVD)*b (MH.cpp:1038):
+// one-sided (Hestenes) Jacobi SVD, singular values <= 2*DBL_EPSILON*sum(w)
+// dropped (OpenCV SVBkSb threshold).
+void pinv3_solve(const std::vector<double>& Ain, const std::vector<double>& b, int m, double* x) {
+  std::vector<double> U(Ain);  // m x 3, columns orthogonalised in place
+  double V[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+  for (int sweep = 0; sweep < 60; ++sweep) {
+    bool changed = false;
+    for (int p = 0; p < 2; ++p)
+      for (int q = p + 1; q < 3; ++q) {
+        double a = 0, bb = 0, g = 0;
+        for (int k = 0; k < m; ++k) {
+          a += U[k * 3 + p] * U[k * 3 + p];
+          bb += U[k * 3 + q] * U[k * 3 + q];
+          g += U[k * 3 + p] * U[k * 3 + q];
+        }
+        if (std::fabs(g) <= DBL_EPSILON * std::sqrt(a * bb) || g == 0.0) continue;
+        changed = true;
+        double zeta = (bb - a) / (2.0 * g);
+        double t = (zeta >= 0 ? 1.0 : -1.0) / (std::fabs(zeta) + std::sqrt(1.0 + zeta * zeta));
+        double c = 1.0 / std::sqrt(1.0 + t * t), s = c * t;
+        for (int k = 0; k < m; ++k) {
+          double up = U[k * 3 + p], uq = U[k * 3 + q];
+          U[k * 3 + p] = c * up - s * uq;
+          U[k * 3 + q] = s * up + c * uq;
+        }
+        for (int k = 0; k < 3; ++k) {
+          double vp = V[k * 3 + p], vq = V[k * 3 + q];
+          V[k * 3 + p] = c * vp - s * vq;
+          V[k * 3 + q] = s * vp + c * vq;
+        }
+      }
+    if (!changed) break;
+  }
+  double w[3], sumw = 0;
+  for (int j = 0; j < 3; ++j) {
+    double s = 0;
+    for (int k = 0; k < m; ++k) s += U[k * 3 + j] * U[k * 3 + j];
+    w[j] = std::sqrt(s);
+    sumw += w[j];
+  }
+  const double thr = 2.0 * DBL_EPSILON * sumw;
+  x[0] = x[1] = x[2] = 0;
+  for (int j = 0; j < 3; ++j) {
+    if (w[j] <= thr) continue;
+    double utb = 0;
+    for (int k = 0; k < m; ++k) utb += U[k * 3 + j] * b[k];
+    const double coef = utb / (w[j] * w[j]);  // (u_j/w_j)^T b / w_j, with u_j = U_j / w_j
+    for (int k = 0; k < 3; ++k) x[k] += V[k * 3 + j] * coef;
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+int orc_hardware_threads() { return (int)std::max(1u, std::thread::hardware_concurrency()); }
+
+void orc_sym_eigen(int n, const double* A, double* evals, double* evecs_rows) { sym_eigen(n, A, evals, evecs_rows); }
+
+void orc_epipole2(const double* F, double* e2 /*2*/) {
+  double e[3];
+  epipole2(F, e);
+  e2[0] = e[0]; e2[1] = e[1];
+}
+
+// ---------------------------------------------------------------------------
+// K1 oracle.  MultiH::ComputeLocalHomographies (MH.cpp:696-717) ->
+// MultiH::GetHomographyHAF (MH.cpp:850-911).  pts: N x (x1 y1 x2 y2), aff:
+// N x (a11 a12 a21 a22), F row-major (x2^T F x1 = 0), e2 = epipole in image 2.
+// Out: N x 9, divided by h33 (MH.cpp:910).
+// ---------------------------------------------------------------------------
+void orc_haf_hypotheses(const double* pts, const double* aff, const double* F, const double* e2, int64_t N, double* H,
+                        int threads) {
+  parallel_for(N, threads, [&](int64_t b, int64_t e) {
+    for (int64_t i = b; i < e; ++i) {
+      double R[6][4], M[16], ev[4], evec[16];
+      haf_rows(pts + 4 * i, aff + 4 * i, F, e2[0], e2[1], R);
+      for (int r = 0; r < 4; ++r)
+        for (int c = 0; c < 4; ++c) {
+          double s = 0;
+          for (int k = 0; k < 6; ++k) s += R[k][r] * R[k][c];
+          M[r * 4 + c] = s;  // A^T A (MH.cpp:890)
+        }
+      sym_eigen(4, M, ev, evec);
+      double* Hi = H + 9 * i;
+      haf_assemble(evec + 12, F, e2[0], e2[1], Hi);  // EVec.row(3) (MH.cpp:895)
+      const double h33 = Hi[8];
+      for (int k = 0; k < 9; ++k) Hi[k] /= h33;  // MH.cpp:910
+    }
+  });
+}
+
+// ---------------------------------------------------------------------------
+// Feature vectors.  10-D: MultiH::EstablishStablePointSets (MH.cpp:612-646),
+// order x1 x2 x3 y1 y2 y3 + locality*(src.x src.y dst.x dst.y).
+// 6-D: MultiH::MergingStep (MH.cpp:359-389), order x1 y1 x2 y2 x3 y3.
+// ---------------------------------------------------------------------------
+void orc_features10(const double* H, const double* pts, double locality, int64_t N, double* out) {
+  for (int64_t i = 0; i < N; ++i) {
+    const double* h = H + 9 * i;
+    const double s1 = h[8], x1 = h[2] / s1, y1 = h[5] / s1;
+    const double s2 = h[6] + h[8], x2 = (h[0] + h[2]) / s2, y2 = (h[3] + h[5]) / s2;
+    const double s3 = h[7] + h[8], x3 = (h[1] + h[2]) / s3, y3 = (h[4] + h[5]) / s3;
+    double* f = out + 10 * i;
+    f[0] = x1; f[1] = x2; f[2] = x3; f[3] = y1; f[4] = y2; f[5] = y3;
+    f[6] = pts[4 * i] * locality; f[7] = pts[4 * i + 1] * locality;
+    f[8] = pts[4 * i + 2] * locality; f[9] = pts[4 * i + 3] * locality;
+  }
+}
+
+void orc_features6(const double* H, int64_t K, double* out) {
+  for (int64_t i = 0; i < K; ++i) {
+    const double* h = H + 9 * i;
+    const double s1 = h[8], x1 = h[2] / s1, y1 = h[5] / s1;
+    const double s2 = h[6] + h[8], x2 = (h[0] + h[2]) / s2, y2 = (h[3] + h[5]) / s2;
+    const double s3 = h[7] + h[8], x3 = (h[1] + h[2]) / s3, y3 = (h[4] + h[5]) / s3;
+    double* f = out + 6 * i;
+    f[0] = x1; f[1] = y1; f[2] = x2; f[3] = y2; f[4] = x3; f[5] = y3;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// K3 oracle.  MeanShiftClustering<double>::Cluster (MS.h:22-157), verbatim
+// semantics: window test = SUM_j |mean_j - x_ij| (L1) < bw^2 (MS.h:76-85);
+// stop when ||mean - old||_2 < 1e-3 bw (MS.h:48,98); merge into the FIRST centre
+// with L2 distance < bw/2 by averaging the two centres and adding votes
+// (MS.h:100-120); final assignment = most votes, first wins ties (MS.h:133-146).
+// Seeds: tempInd = round(rnd * (remaining-1)), rnd = rand()/RAND_MAX (MS.h:54-56).
+// The injected generator restates MSVC's rand() (the reference is an MSVC
+// program): holdrand = holdrand*214013 + 2531011, (holdrand>>16)&0x7fff,
+// RAND_MAX 32767; *rng_state carries holdrand across calls (initially 1).
+// metric: 0 = L1_REF (reference), 1 = L2 (||.||_2^2 < bw^2; the tensor-core variant).
+// Returns the number of centres C; centres: up to max_c x D; assign: N (−1 never
+// occurs unless no votes); votes_out optional.  Also reports trajectory and
+// window-iteration counts.
+// ---------------------------------------------------------------------------
+int orc_meanshift(const double* data, int N, int D, double bw, int metric, uint32_t* rng_state, double* centres,
+                  int max_c, int* assign, int64_t* stats /*[2]: trajectories, iterations*/) {
+  const double bandSq = bw * bw, stopThresh = 1e-3 * bw;
+  std::vector<int> initPtInds(N);
+  std::vector<char> visited(N, 0);
+  for (int i = 0; i < N; ++i) initPtInds[i] = i;
+  std::vector<std::vector<double>> clustCent;
+  std::vector<std::vector<int>> clusterVotes;
+  int64_t traj = 0, iters = 0;
+  uint32_t hold = rng_state ? *rng_state : 1u;
+  std::vector<double> myMean(D), oldMean(D), acc(D);
+  while (!initPtInds.empty()) {
+    hold = hold * 214013u + 2531011u;
+    const int r = (int)((hold >> 16) & 0x7fff);
+    const double rnd = r / 32767.0;
+    const int tempInd = (int)std::round(rnd * (double)(initPtInds.size() - 1));
+    const int stInd = initPtInds[tempInd];
+    for (int j = 0; j < D; ++j) myMean[j] = data[(size_t)stInd * D + j];
+    std::vector<int> votes(N, 0);
+    ++traj;
+    while (true) {
+      ++iters;
+      oldMean = myMean;
+      std::fill(acc.begin(), acc.end(), 0.0);
+      int cnt = 0;
+      for (int i = 0; i < N; ++i) {
+        const double* x = data + (size_t)i * D;
+        double s = 0;
+        if (metric == 0)
+          for (int j = 0; j < D; ++j) { double d = oldMean[j] - x[j]; s += std::sqrt(d * d); }
+        else
+          for (int j = 0; j < D; ++j) { double d = oldMean[j] - x[j]; s += d * d; }
+        if (s < bandSq) {
+          ++votes[i]; ++cnt; visited[i] = 1;
+          for (int j = 0; j < D; ++j) acc[j] += x[j];
+        }
+      }
+      for (int j = 0; j < D; ++j) myMean[j] = acc[j] / cnt;  // cnt==0 -> NaN as in the reference (cannot occur: seed is a member)
+      double n2 = 0;
+      for (int j = 0; j < D; ++j) n2 += (myMean[j] - oldMean[j]) * (myMean[j] - oldMean[j]);
+      if (std::sqrt(n2) < stopThresh) {
+        int mergeWith = -1;
+        for (size_t cn = 0; cn < clustCent.size(); ++cn) {
+          double d2 = 0;
+          for (int j = 0; j < D; ++j) d2 += (myMean[j] - clustCent[cn][j]) * (myMean[j] - clustCent[cn][j]);
+          if (std::sqrt(d2) < bw / 2) { mergeWith = (int)cn; break; }
+        }
+        if (mergeWith > -1) {
+          for (int j = 0; j < D; ++j) clustCent[mergeWith][j] = 0.5 * (clustCent[mergeWith][j] + myMean[j]);
+          for (int i = 0; i < N; ++i) clusterVotes[mergeWith][i] += votes[i];
+        } else {
+          clustCent.push_back(myMean);
+          clusterVotes.push_back(votes);
+        }
+        break;
+      }
+      if (iters > 100000000) break;  // guard only
+    }
+    initPtInds.clear();
+    for (int i = 0; i < N; ++i)
+      if (!visited[i]) initPtInds.push_back(i);
+  }
+  std::vector<int> best(N, 0);
+  for (int i = 0; i < N; ++i) assign[i] = -1;
+  for (size_t r = 0; r < clusterVotes.size(); ++r)
+    for (int i = 0; i < N; ++i)
+      if (best[i] < clusterVotes[r][i]) { best[i] = clusterVotes[r][i]; assign[i] = (int)r; }
+  const int C = (int)clustCent.size();
+  for (int c = 0; c < C && c < max_c; ++c)
+    for (int j = 0; j < D; ++j) centres[(size_t)c * D + j] = clustCent[c][j];
+  if (rng_state) *rng_state = hold;
+  if (stats) { stats[0] = traj; stats[1] = iters; }
+  return C;
+}
+
+void orc_normalize_points(const double* pts, int n, double* out, double* T) { normalize_points(pts, n, out, T); }
+
+// ---------------------------------------------------------------------------
+// K4 (3PT) oracle.  MultiH::GetHomography3PT (MH.cpp:995-1055) with
+// do_numerical_refinement=false (the LM callback is not a parity target, see
+// SURVEY.md §8a row 8).  pts1/pts2: n x 2.  Out H (3x3, NOT divided by h33).
+// ---------------------------------------------------------------------------
+void orc_homography_3pt(const double* pts1, const double* pts2, int n, const double* F, double* H) {
+  std::vector<double> n1(2 * n), n2(2 * n);
+  double T1[9], T2[9], T1i[9], T2i[9];
+  normalize_points(pts1, n, n1.data(), T1);
+  normalize_points(pts2, n, n2.data(), T2);
+  inv_similarity(T1, T1i);
+  inv_similarity(T2, T2i);
+  double T2it[9];
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) T2it[i * 3 + j] = T2i[j * 3 + i];
+  double Fn[9];
+  mat3_mul(T2it, F, Fn);
+  mat3_mul(Fn, T1i, Fn);  // MH.cpp:1009
+  double e[3];
+  epipole2(Fn, e);  // MH.cpp:1013-1017
+  std::vector<double> A(6 * n), b(2 * n);
+  for (int i = 0; i < n; ++i) {
+    const double x1 = n1[2 * i], y1 = n1[2 * i + 1], x2 = n2[2 * i], y2 = n2[2 * i + 1];
+    A[6 * i + 0] = e[0] * x1 - x2 * x1; A[6 * i + 1] = e[0] * y1 - x2 * y1; A[6 * i + 2] = e[0] - x2;
+    A[6 * i + 3] = e[1] * x1 - y2 * x1; A[6 * i + 4] = e[1] * y1 - y2 * y1; A[6 * i + 5] = e[1] - y2;
+    b[2 * i] = -(x1 * Fn[3] + y1 * Fn[4] + Fn[5]);
+    b[2 * i + 1] = (x1 * Fn[0] + y1 * Fn[1] + Fn[2]);
+  }
+  double h3[3];
+  pinv3_solve(A, b, 2 * n, h3);  // MH.cpp:1038
+  double Hn[9];
+  const double v[4] = {h3[0], h3[1], h3[2], 1.0};  // lambda == 1 (MH.cpp:1045-1050)
+  haf_assemble(v, Fn, e[0], e[1], Hn);
+  mat3_mul(T2i, Hn, Hn);
+  mat3_mul(Hn, T1, H);  // MH.cpp:1054
+}
+
+// Batched form used by EstablishStablePointSets (MH.cpp:664-688): one 3PT fit
+// per cluster over the members listed in CSR (offsets[C+1], members[]).
+// Clusters with < 3 members get keep[c]=0 (MH.cpp:667).
+void orc_cluster_3pt(const double* pts, const int* offsets, const int* members, int C, const double* F, double* H,
+                     int* keep) {
+  for (int c = 0; c < C; ++c) {
+    const int n = offsets[c + 1] - offsets[c];
+    keep[c] = n >= 3;
+    if (n < 3) continue;
+    std::vector<double> p1(2 * n), p2(2 * n);
+    for (int j = 0; j < n; ++j) {
+      const double* p = pts + 4 * (size_t)members[offsets[c] + j];
+      p1[2 * j] = p[0]; p1[2 * j + 1] = p[1]; p2[2 * j] = p[2]; p2[2 * j + 1] = p[3];
+    }
+    orc_homography_3pt(p1.data(), p2.data(), n, F, H + 9 * c);
+  }
+}
+
+// MergingStep's mode -> homography (MH.cpp:408-427): 3PT on (0,0),(1,0),(0,1)
+// and the mode's 6-D feature (x1 y1 x2 y2 x3 y3).
+void orc_mode_to_homography(const double* mode6, const double* F, double* H) {
+  const double p1[6] = {0, 0, 1, 0, 0, 1};
+  orc_homography_3pt(p1, mode6, 3, F, H);
+}
+
+// ---------------------------------------------------------------------------
+// K2 oracle.  dataEnergy (MH.cpp:473-504) + EnergyDataStruct (MH.h:23-47),
+// evaluated densely: out[p*(K+1)+l], l=0 is the outlier label.
+// lambda = spatial weight (0.5), thr = homography threshold (2.2 px).
+// ---------------------------------------------------------------------------
+int orc_data_cost(const double* p /*x1 y1 x2 y2*/, const double* h /*9 or null for l==0*/, double lambda, double thr) {
+  const double lam = 100.0 / lambda;              // one_per_energy_lambda (MH.h:42)
+  const double T = thr * thr * 81.0 / 16.0;       // truncated_sqr_threshold (MH.h:44)
+  if (!h) return c_round(lam * T);                // MH.cpp:478-479
+  const double s1 = h[6] * p[0] + h[7] * p[1] + h[8];
+  const double x1 = (h[0] * p[0] + h[1] * p[1] + h[2]) / s1;
+  const double y1 = (h[3] * p[0] + h[4] * p[1] + h[5]) / s1;
+  const double dx = x1 - p[2], dy = y1 - p[3];
+  const double distance = dx * dx + dy * dy;
+  if (distance < T) return c_round(lam * (1.0f - (distance / T)));  // MH.cpp:501-502
+  return 2 * c_round(lam * T);                                       // MH.cpp:503
+}
+
+void orc_residuals(const double* pts, int64_t N, const double* H, int K, double* d2 /*N x K*/, int threads) {
+  parallel_for(N, threads, [&](int64_t b, int64_t e) {
+    for (int64_t i = b; i < e; ++i) {
+      const double* p = pts + 4 * i;
+      for (int l = 0; l < K; ++l) {
+        const double* h = H + 9 * (size_t)l;
+        const double s1 = h[6] * p[0] + h[7] * p[1] + h[8];
+        const double x1 = (h[0] * p[0] + h[1] * p[1] + h[2]) / s1;
+        const double y1 = (h[3] * p[0] + h[4] * p[1] + h[5]) / s1;
+        const double dx = x1 - p[2], dy = y1 - p[3];
+        d2[i * K + l] = dx * dx + dy * dy;
+      }
+    }
+  });
+}
+
+void orc_data_cost_dense(const double* pts, int64_t N, const double* H, int K, double lambda, double thr, int32_t* out,
+                         int threads) {
+  parallel_for(N, threads, [&](int64_t b, int64_t e) {
+    for (int64_t i = b; i < e; ++i) {
+      int32_t* o = out + i * (K + 1);
+      o[0] = orc_data_cost(pts + 4 * i, nullptr, lambda, thr);
+      for (int l = 0; l < K; ++l) o[l + 1] = orc_data_cost(pts + 4 * i, H + 9 * (size_t)l, lambda, thr);
+    }
+  });
+}
+
+// Throughput form for the CPU baseline: evaluates dataEnergy over N x K without
+// materialising the matrix; returns a checksum (sum of costs) so the work cannot
+// be elided, plus per-point argmin label (0 = outlier) and per-hypothesis inlier
+// counts at d2 < thr^2 (the quantities the fused GPU kernel emits).
+int64_t orc_data_cost_sweep(const double* pts, int64_t N, const double* H, int K, double lambda, double thr,
+                            int32_t* argmin_label /*N or null*/, int64_t* inlier_count /*K or null*/, int threads) {
+  std::atomic<int64_t> total{0};
+  std::vector<std::vector<int64_t>> counts(threads > 0 ? threads : 1, std::vector<int64_t>(inlier_count ? K : 0, 0));
+  const double thr2 = thr * thr;
+  int64_t chunk = (N + std::max(threads, 1) - 1) / std::max(threads, 1);
+  parallel_for(N, threads, [&](int64_t b, int64_t e) {
+    const int tid = chunk > 0 ? (int)(b / chunk) : 0;
+    int64_t local = 0;
+    for (int64_t i = b; i < e; ++i) {
+      const double* p = pts + 4 * i;
+      int best = orc_data_cost(p, nullptr, lambda, thr), bestl = 0;
+      local += best;
+      for (int l = 0; l < K; ++l) {
+        const double* h = H + 9 * (size_t)l;
+        const int c = orc_data_cost(p, h, lambda, thr);
+        local += c;
+        if (c < best) { best = c; bestl = l + 1; }
+        if (inlier_count) {
+          const double s1 = h[6] * p[0] + h[7] * p[1] + h[8];
+          const double x1 = (h[0] * p[0] + h[1] * p[1] + h[2]) / s1;
+          const double y1 = (h[3] * p[0] + h[4] * p[1] + h[5]) / s1;
+          const double dx = x1 - p[2], dy = y1 - p[3];
+          if (dx * dx + dy * dy < thr2) ++counts[tid][l];
+        }
+      }
+      if (argmin_label) argmin_label[i] = bestl;
+    }
+    total += local;
+  });
+  if (inlier_count)
+    for (int l = 0; l < K; ++l) {
+      int64_t s = 0;
+      for (auto& c : counts) s += c[l];
+      inlier_count[l] = s;
+    }
+  return total.load();
+}
+
+int orc_smooth_cost(int l1, int l2, double lambda) { return l1 != l2 ? c_round(100.0 * lambda) : 0; }  // MH.cpp:506-511
+
+// ---------------------------------------------------------------------------
+// MergingStep inlier scan + straightness test (MH.cpp:430-463) for K' candidate
+// homographies: count[k] = #{d2 < thr^2}; scatter[k] = 6 uniques of
+// S = SUM_inl [x y 1]^T [x y 1] (xx xy x yy y n); lambda_min[k] = smallest
+// eigenvalue of S; keep[k] = !(lambda_min < straightness || count < 3).
+// ---------------------------------------------------------------------------
+void orc_inlier_stats(const double* pts, int64_t N, const double* H, int K, double thr, double straightness,
+                      int64_t* count, double* scatter6, double* lambda_min, int* keep) {
+  const double thr2 = thr * thr;
+  for (int k = 0; k < K; ++k) {
+    const double* h = H + 9 * (size_t)k;
+    double sxx = 0, sxy = 0, sx = 0, syy = 0, sy = 0;
+    int64_t n = 0;
+    for (int64_t j = 0; j < N; ++j) {
+      const double* p = pts + 4 * j;
+      const double s = h[6] * p[0] + h[7] * p[1] + h[8];
+      const double x1 = (h[0] * p[0] + h[1] * p[1] + h[2]) / s;
+      const double y1 = (h[3] * p[0] + h[4] * p[1] + h[5]) / s;
+      const double dx = p[2] - x1, dy = p[3] - y1;
+      if (dx * dx + dy * dy < thr2) {
+        ++n; sxx += p[0] * p[0]; sxy += p[0] * p[1]; sx += p[0]; syy += p[1] * p[1]; sy += p[1];
+      }
+    }
+    const double S[9] = {sxx, sxy, sx, sxy, syy, sy, sx, sy, (double)n};
+    double ev[3], evec[9];
+    sym_eigen(3, S, ev, evec);
+    if (count) count[k] = n;
+    if (scatter6) { double* o = scatter6 + 6 * k; o[0] = sxx; o[1] = sxy; o[2] = sx; o[3] = syy; o[4] = sy; o[5] = (double)n; }
+    if (lambda_min) lambda_min[k] = ev[2];
+    if (keep) keep[k] = !(ev[2] < straightness || n < 3);
+  }
+}
+
+// ComputeInliersOfHomography (MH.cpp:743-768): labels[i] = idx where d2 < thr^2.
+void orc_inliers_of_homography(const double* pts, int64_t N, const double* h, double thr, int idx, int32_t* labels) {
+  const double thr2 = thr * thr;
+  for (int64_t i = 0; i < N; ++i) {
+    const double* p = pts + 4 * i;
+    const double s = h[6] * p[0] + h[7] * p[1] + h[8];
+    const double x1 = (h[0] * p[0] + h[1] * p[1] + h[2]) / s;
+    const double y1 = (h[3] * p[0] + h[4] * p[1] + h[5]) / s;
+    const double dx = x1 - p[2], dy = y1 - p[3];
+    if (dx * dx + dy * dy < thr2) labels[i] = idx;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// K4 (HAF) oracle.  LabelingStep's per-label gather (MH.cpp:545-584) +
+// MultiH::GetHomographyHAFNonminimal (MH.cpp:913-990) with
+// do_numerical_refinement=false.  labels: N ints in −1..K−1 (−1 = outlier).
+// Out: H[K][9] (NOT divided by h33), M10[K][10] = upper triangle of
+// SUM_i A_i^T A_i (row-major uniques 00 01 02 03 11 12 13 22 23 33), count[K].
+// Labels with no member keep H untouched (MH.cpp:592-593).
+// ---------------------------------------------------------------------------
+void orc_refit_haf(const double* pts, const double* aff, const int32_t* labels, int64_t N, int K, const double* F,
+                   const double* e2, double* H, double* M10, int64_t* count) {
+  std::vector<double> M((size_t)K * 16, 0.0);
+  std::vector<int64_t> cnt(K, 0);
+  for (int64_t i = 0; i < N; ++i) {
+    const int l = labels[i];
+    if (l < 0 || l >= K) continue;
+    double R[6][4];
+    haf_rows(pts + 4 * i, aff + 4 * i, F, e2[0], e2[1], R);
+    double* m = M.data() + 16 * (size_t)l;
+    for (int r = 0; r < 4; ++r)
+      for (int c = 0; c < 4; ++c) {
+        double s = 0;
+        for (int k = 0; k < 6; ++k) s += R[k][r] * R[k][c];
+        m[r * 4 + c] += s;
+      }
+    ++cnt[l];
+  }
+  for (int l = 0; l < K; ++l) {
+    const double* m = M.data() + 16 * (size_t)l;
+    if (M10) {
+      double* o = M10 + 10 * (size_t)l;
+      int q = 0;
+      for (int r = 0; r < 4; ++r)
+        for (int c = r; c < 4; ++c) o[q++] = m[r * 4 + c];
+    }
+    if (count) count[l] = cnt[l];
+    if (cnt[l] == 0) continue;
+    double ev[4], evec[16];
+    sym_eigen(4, m, ev, evec);
+    haf_assemble(evec + 12, F, e2[0], e2[1], H + 9 * (size_t)l);
+  }
+}
+
+// Exact 4-D radius neighbourhood (restating the INTENT of MH.cpp:231-253:
+// FlannBasedMatcher::radiusMatch on float (x1,y1,x2,y2) with maxDistance =
+// 1/locality; OpenCV squares maxDistance for the L2 FLANN index.  FLANN's
+// default KD-tree search is approximate; the oracle uses the exact set, see
+// SURVEY.md appendix).  Returns CSR; self excluded (MH.cpp:537).
+// Call with adj == null to get the total count first.
+int64_t orc_radius_neighbours(const double* pts, int N, double radius, int64_t* offsets /*N+1*/, int32_t* adj) {
+  const float r2 = (float)(radius * radius);
+  int64_t total = 0;
+  for (int i = 0; i < N; ++i) {
+    if (offsets) offsets[i] = total;
+    const float a0 = (float)pts[4 * i], a1 = (float)pts[4 * i + 1], a2 = (float)pts[4 * i + 2], a3 = (float)pts[4 * i + 3];
+    for (int j = 0; j < N; ++j) {
+      if (j == i) continue;
+      const float d0 = a0 - (float)pts[4 * j], d1 = a1 - (float)pts[4 * j + 1], d2 = a2 - (float)pts[4 * j + 2],
+                  d3 = a3 - (float)pts[4 * j + 3];
+      if (d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3 <= r2) {
+        if (adj) adj[total] = j;
+        ++total;
+      }
+    }
+  }
+  if (offsets) offsets[N] = total;
+  return total;
+}
+
+}  // extern "C"
