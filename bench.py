@@ -1,0 +1,349 @@
+#!/usr/bin/env python
+"""bench.py — the Multi-H hot path on B200 (BASELINE.json metric: correspondence x hypothesis residuals/s).
+
+Workload (config.workload = "cfg4"): BASELINE.json configs[3], the configuration the metric is quoted on — synthetic
+200-plane scene, 4 194 304 affine correspondences x 8192 hypotheses (200 generating homographies + 7992 HAF hypotheses
+of randomly chosen correspondences), correspondence-sharded over the ranks (strong scaling: the scene is fixed).
+
+One "step" = one pass of the hot path over the scene:
+    K1  HAF hypothesis per correspondence                    (MultiH.cpp:696-717, 850-911)
+    [N>1] NCCL broadcast of the 8192 x 12 hypothesis block from rank 0
+    K2  fused N x K residual / data cost: per-site data-term argmin label + cost, per-site in-range count,
+        per-hypothesis inlier count — nothing N x K touches HBM (MultiH.cpp:473-504, 430-443, 743-768)
+    [N>1] NCCL all-reduce of the K inlier counts
+    K4  per-label refit statistics from the argmin labels (segmented reduction of SUM A^T A)
+    [N>1] NCCL all-reduce of the K x 12 FP64 statistics
+    K4  batched 4x4 eigen-solves -> refined homographies      (MultiH.cpp:545-599, 913-990)
+`value` times that with the inputs resident in HBM; `e2e` times the same pass through the C ABI from PINNED HOST
+buffers (H2D of the FP64 correspondences + affines, normalisation, the pass, D2H of labels + refined homographies).
+
+--impl reference times the reference's CPU implementation of the same path: the reference is an MSVC/OpenCV-3.1
+program that cannot be built here, so this is the FP64 oracle port (oracle/multih_oracle.cpp), threaded over
+the loops the reference parallelises with PPL, on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_TOTAL = 4 * (1 << 20)
+N_PLANES = 200
+K_HYP = 8192
+SEED = 0xB200 + 3
+FLOP_PER_RESIDUAL = 20
+
+
+def make_workload(n_total=N_TOTAL):
+    import multih_b200 as m
+
+    sc = m.scenes.make_scene(n_total, N_PLANES, seed=SEED)
+    rng = np.random.Generator(np.random.Philox(SEED + 1))
+    pick = rng.integers(0, n_total, size=K_HYP - N_PLANES)
+    return sc, pick
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi style clock / throttle sampling during the timed region (via NVML)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.sm, self.reasons, self.max_mhz = index, False, [], set(), None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+                 nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap"}
+        while not self.stop_flag:
+            try:
+                self.sm.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.05)
+
+    def summary(self):
+        return {"sm_mhz": (float(np.median(self.sm)) if self.sm else None), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.sm)}
+
+
+def run_reference(args):
+    """CPU arm: oracle port of dataEnergy swept densely over a bounded sample of cfg4 (argmin + inlier counts)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle as orc
+
+    n_sample = 16384
+    sc, pick = make_workload(1 << 18)
+    cores = orc.hardware_threads()
+    hyp = np.concatenate([sc.planes, orc.haf_hypotheses(sc.pts[pick % len(sc.pts)], sc.aff[pick % len(sc.pts)], sc.F,
+                                                        threads=cores)])
+    pts = sc.pts[:n_sample]
+    for _ in range(args.warmup):
+        orc.data_cost_sweep(pts[:2048], hyp, threads=cores)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        orc.data_cost_sweep(pts, hyp, threads=cores)
+    dt = time.perf_counter() - t0
+    value = n_sample * K_HYP * args.steps / dt
+    line = {
+        "impl": "reference", "metric": "correspondence x hypothesis residual evaluations per second", "value": value,
+        "unit": "residuals/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "cfg4: synthetic 200-plane scene, 4M correspondences x 8192 hypotheses "
+                               "(bounded sample per step)", "hypotheses": K_HYP},
+        "cpu_baseline": {"value": value, "unit": "residuals/s", "cores": cores, "kind": "port",
+                         "sample": f"{n_sample} correspondences x {K_HYP} hypotheses per step (dataEnergy + argmin + "
+                                   f"inlier count, FP64 oracle port, {cores} threads)"},
+        "e2e": {"value": value, "unit": "residuals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n-total", type=int, default=N_TOTAL)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    import multih_b200 as m
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+
+    # ---- workload ----------------------------------------------------------------------------------------------------
+    n_total = args.n_total
+    sc, pick = make_workload(n_total)
+    lo, hi = m.dist.shard_range(n_total, rank, world)
+    n_loc = hi - lo
+    ctx = m.Context(device=local)
+    ctx.set_geometry(sc.F, sc.pts)  # same strided sample on every rank -> identical normalisation
+    h_pts = torch.from_numpy(sc.pts[lo:hi]).pin_memory()
+    h_aff = torch.from_numpy(sc.aff[lo:hi]).pin_memory()
+    d_pts, d_aff = ctx.upload(h_pts, h_aff)
+    # hypothesis block: rank 0 builds it (K1 on the picked correspondences), then it is broadcast every step
+    d_hyp = torch.zeros((K_HYP, 12), dtype=torch.float32, device=dev)
+    if rank == 0:
+        p_pts, p_aff = ctx.upload(sc.pts[pick], sc.aff[pick])
+        d_hyp[:N_PLANES] = ctx.hypotheses_from_host(sc.planes)
+        d_hyp[N_PLANES:] = ctx.haf_hypotheses(p_pts, p_aff)
+        del p_pts, p_aff
+    d_hyp_pt = torch.empty((n_loc, 12), dtype=torch.float32, device=dev)
+    fused = {"count": torch.empty(n_loc, dtype=torch.int32, device=dev),
+             "best": torch.empty(n_loc, dtype=torch.int64, device=dev),
+             "inliers": torch.empty(K_HYP, dtype=torch.int32, device=dev)}
+    labels = torch.empty(n_loc, dtype=torch.int32, device=dev)
+    acc = torch.empty((K_HYP, 12), dtype=torch.float64, device=dev)
+    d_ref = torch.empty((K_HYP, 12), dtype=torch.float32, device=dev)
+    h_labels = torch.empty(n_loc, dtype=torch.int32).pin_memory()
+    h_ref = torch.empty((K_HYP, 12), dtype=torch.float32).pin_memory()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    k2_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+             for _ in range(args.steps + args.warmup + 1)]
+
+    def hot_pass(ev=None):
+        ctx.haf_hypotheses(d_pts, d_aff, out=d_hyp_pt)                                      # K1
+        if world > 1:
+            dist.broadcast(d_hyp, src=0)
+        if ev is not None:
+            ev[0].record()
+        ctx.data_cost_fused(d_pts, d_hyp, kmax=0, want_list=False, out=fused)                # K2
+        if ev is not None:
+            ev[1].record()
+        if world > 1:
+            dist.all_reduce(fused["inliers"])
+        torch.bitwise_and(fused["best"], 0xFFFFFFFF, out=fused["best"])                      # label = low word
+        labels.copy_(fused["best"]); labels.sub_(1)                                          # -1 = outlier
+        d_ref.copy_(d_hyp)
+        ctx.refit_haf_accumulate(d_pts, d_aff, labels, K_HYP, out=acc)                       # K4 statistics
+        if world > 1:
+            dist.all_reduce(acc)
+        ctx.refit_haf_solve(acc, d_ref)                                                      # K4 solves
+
+    def e2e_pass():
+        ctx.upload(h_pts, h_aff, out=(d_pts, d_aff))                                         # H2D + normalise
+        hot_pass()
+        h_labels.copy_(labels, non_blocking=True)                                            # D2H results
+        h_ref.copy_(d_ref, non_blocking=True)
+        torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing ------------------------------------------------------------------------------------------
+    for i in range(args.warmup):
+        hot_pass(k2_ev[i])
+        flush.zero_()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches0 = ctx.launches
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for i in range(args.steps):
+        hot_pass(k2_ev[args.warmup + i])
+        flush.zero_()  # L2 flush between timed iterations (inside the timed region; ~40 us per step)
+    t1.record()
+    barrier()
+    sampler.stop_flag = True
+    launches = ctx.launches - launches0
+    ms_total = t0.elapsed_time(t1)
+    k2_ms = float(np.mean([a.elapsed_time(b) for a, b in k2_ev[args.warmup:args.warmup + args.steps]]))
+    t = torch.tensor([ms_total, k2_ms], dtype=torch.float64, device=dev)
+    lt = torch.tensor([launches], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(lt)
+    ms_total, k2_ms = float(t[0]), float(t[1])
+    ms_per_step = ms_total / args.steps
+    value = n_total * K_HYP / (ms_per_step * 1e-3)
+
+    # ---- end-to-end timing (host buffers) -----------------------------------------------------------------------------------
+    for _ in range(2):
+        e2e_pass()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        e2e_pass()
+    e1.record()
+    barrier()
+    te = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = n_total * K_HYP / (float(te[0]) / args.steps * 1e-3)
+    h2d = (h_pts.numel() + h_aff.numel()) * 8 * world
+    d2h = (h_labels.numel() * 4) * world + h_ref.numel() * 4 * world
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (K2 fused): FP32 CUDA-core pipe --------------------------------------------------------
+    peak_scalar = max(ctx.fp32_peak(0, 20000) for _ in range(3))
+    peak_packed = max(ctx.fp32_peak(1, 20000) for _ in range(3))
+    peak = max(peak_scalar, peak_packed)
+    achieved = FLOP_PER_RESIDUAL * (n_loc * K_HYP) / (k2_ms * 1e-3) / 1e12
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "k2_fused_traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {"bound": "fp32", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                "traffic": traffic, "kernel": "cost_fused_kernel",
+                "algorithmic": f"{FLOP_PER_RESIDUAL} flop/residual x {n_loc} x {K_HYP} per launch",
+                "kernel_ms": k2_ms, "kernel_share_of_step": k2_ms / ms_per_step,
+                "peak_source": "measured in this run: dependent-FFMA probe (mh_diag_fp32_peak), "
+                               f"scalar FFMA {peak_scalar:.1f} / packed FFMA2 {peak_packed:.1f} TFLOP/s; "
+                               "MEASURED_PEAKS.json carries only HBM and bf16-tensor peaks; nominal 148 SM x 128 lanes x "
+                               "2 x 1.965 GHz = 74.4"}
+    # the HBM-bound variant of the same kernel family (dense int16 cost matrix), timed alone for the record
+    kd = 1024
+    nd = min(n_loc, 1 << 20)
+    od = torch.empty((nd, kd + 1), dtype=torch.int16, device=dev)
+    for _ in range(2):
+        ctx.data_cost_dense(d_pts[:nd], d_hyp[:kd], elem_bytes=2, out=od)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(3):
+        ctx.data_cost_dense(d_pts[:nd], d_hyp[:kd], elem_bytes=2, out=od)
+    b.record()
+    torch.cuda.synchronize()
+    dense_ms = a.elapsed_time(b) / 3
+    hbm_peak = None
+    try:
+        hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+    except Exception:
+        hbm_peak = 6650.0
+    dense_gbs = nd * (kd + 1) * 2 / (dense_ms * 1e-3) / 1e9
+    roofline_dense = {"bound": "hbm", "achieved": dense_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": dense_gbs / hbm_peak,
+                      "traffic": None, "kernel": "cost_dense_kernel<int16>",
+                      "algorithmic": f"2 B/residual x {nd} x {kd + 1} per launch", "kernel_ms": dense_ms}
+
+    # ---- CPU baseline (oracle port) on a bounded sample -----------------------------------------------------------------------
+    cpu = None
+    if not args.no_cpu_baseline:
+        from oracle import oracle as orc
+
+        cores = orc.hardware_threads()
+        ns = 16384
+        hyp_host = ctx.hypotheses_to_host(d_hyp)
+        orc.data_cost_sweep(sc.pts[:1024], hyp_host, threads=cores)
+        reps, tc = 0, time.perf_counter()
+        while time.perf_counter() - tc < 10.0 or reps < 1:
+            orc.data_cost_sweep(sc.pts[:ns], hyp_host, threads=cores)
+            reps += 1
+        dtc = time.perf_counter() - tc
+        cpu = {"value": ns * K_HYP * reps / dtc, "unit": "residuals/s", "cores": cores, "kind": "port",
+               "sample": f"{reps} x ({ns} correspondences x {K_HYP} hypotheses) of the same scene, FP64 oracle port of "
+                         f"dataEnergy + argmin + inlier count, {cores} threads, {dtc:.1f} s"}
+
+    line = {
+        "metric": "correspondence x hypothesis residual evaluations per second (whole job)",
+        "value": value, "unit": "residuals/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "cfg4: synthetic 200-plane scene, 4M affine correspondences x 8192 hypotheses "
+                               "(200 planes + 7992 HAF hypotheses), correspondence-sharded",
+                   "correspondences": n_total, "hypotheses": K_HYP, "per_rank": n_loc,
+                   "step": "K1 HAF + K2 fused cost/argmin/inlier-count + K4 refit (+ NCCL bcast/all-reduce for N>1)",
+                   "l2": "256 MiB memset between steps, inside the timed region"},
+        "clocks": sampler.summary(),
+        "e2e": {"value": e2e_value, "unit": "residuals/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": float(te[0]) / args.steps},
+        "gpu_launches": int(lt[0]),
+        "roofline": roofline, "roofline_dense": roofline_dense, "cpu_baseline": cpu,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -61,6 +61,8 @@ typedef struct mh_params {
   int32_t meanshift_metric; /* 0 = L1_REF (MeanShiftClustering.h:76-85), 1 = L2                */
   uint32_t rng_seed;      /* state of the injected MSVC-rand() restatement (1 = unseeded rand) */
   int32_t max_gc_cycles;  /* expansion(iter, 1000)  (MultiH.cpp:543)                           */
+  int32_t max_neighbours; /* 31: FLANN default checks=32 caps radiusMatch (MultiH.cpp:252-253) at the ~31 nearest
+                             other sites inside the radius; <= 0 = the full radius ball                      */
 } mh_params;
 
 void mh_default_params(mh_params* p); /* main.cpp:55-59: 2.6 / 2.2 / 0.005 / 0.5 / 20 */
@@ -99,7 +101,8 @@ mh_status mh_hypotheses_to_host(mh_ctx* ctx, const void* d_hyp, int32_t K, doubl
 
 /* ---- K1: per-correspondence HAF hypotheses ------------------------------
  * MultiH::ComputeLocalHomographies (MultiH.cpp:696-717) -> GetHomographyHAF (:850-911).
- * precision: 0 = FP32 one-sided Jacobi on the 6x4 system (default), 1 = FP64 A^T A + Jacobi. */
+ * Solved in pixel coordinates in FP64 (A^T A + cyclic Jacobi, as the reference) — the least-squares estimate is not
+ * invariant to normalisation.  `precision` is reserved (0). */
 mh_status mh_haf_hypotheses(mh_ctx* ctx, const void* d_pts, const void* d_aff, int64_t N, void* d_hyp,
                             int32_t precision);
 
@@ -146,6 +149,12 @@ mh_status mh_meanshift(mh_ctx* ctx, const void* d_feat, int32_t N, int32_t D, do
  * (MultiH.cpp:592-593).  d_count i32 [K] optional. */
 mh_status mh_refit_haf(mh_ctx* ctx, const void* d_pts, const void* d_aff, const void* d_labels, int64_t N, int32_t K,
                        void* d_hyp, void* d_count);
+/* The same refit split at its reduction point, for correspondence-sharded multi-GPU runs: accumulate writes, per label,
+ * the 10 uniques of SUM A_i^T A_i (FP64, pixel coordinates), the member count ([10]) and a pad ([11]) into
+ * d_acc f64 [K][12]; shards all-reduce(sum) that array; solve does the batched 4x4 eigen-solves. */
+mh_status mh_refit_haf_accumulate(mh_ctx* ctx, const void* d_pts, const void* d_aff, const void* d_labels, int64_t N,
+                                  int32_t K, void* d_acc);
+mh_status mh_refit_haf_solve(mh_ctx* ctx, const void* d_acc, int32_t K, void* d_hyp, void* d_count);
 /* GetHomography3PT (MultiH.cpp:995-1055, linear solution) per cluster of EstablishStablePointSets (:664-688):
  * d_assign i32 [N] in -1..C-1; clusters with < 3 members get keep=0 (:667). */
 mh_status mh_refit_3pt(mh_ctx* ctx, const void* d_pts, const void* d_assign, int64_t N, int32_t C, void* d_hyp,
@@ -154,10 +163,11 @@ mh_status mh_refit_3pt(mh_ctx* ctx, const void* d_pts, const void* d_assign, int
 mh_status mh_modes_to_hypotheses(mh_ctx* ctx, const void* d_modes /*f64 [C][6]*/, int32_t C, void* d_hyp);
 
 /* ---- host combinatorial steps (consume GPU-built costs) ------------------- */
-/* Exact 4-D radius neighbourhood replacing FlannBasedMatcher::radiusMatch (MultiH.cpp:231-253). CSR out; call with
- * adj_host == NULL to size. */
-mh_status mh_neighbourhood(mh_ctx* ctx, const double* pts_host, int32_t N, double radius, int64_t* offsets_host,
-                           int32_t* adj_host, int64_t* total_out);
+/* 4-D neighbourhood replacing FlannBasedMatcher::radiusMatch (MultiH.cpp:231-253): per site the `max_neighbours`
+ * nearest other sites (ties by index) with d^2 <= radius^2 on float (x1,y1,x2,y2); <= 0 = full ball.  Directed CSR out,
+ * ascending neighbour index; call with adj_host == NULL to size.  Host-only: ctx may be NULL. */
+mh_status mh_neighbourhood(mh_ctx* ctx, const double* pts_host, int32_t N, double radius, int32_t max_neighbours,
+                           int64_t* offsets_host, int32_t* adj_host, int64_t* total_out);
 /* Alpha-expansion (the role of GCoptimizationGeneralGraph in MultiH.cpp:520-543; own implementation, int64 totals):
  * dense site-major int32 costs [N][L], Potts weight per DIRECTED adjacency entry. */
 mh_status mh_alpha_expansion(mh_ctx* ctx, const int32_t* cost_host, int32_t N, int32_t L, int32_t potts,
@@ -177,6 +187,12 @@ int32_t mh_get_iterations(const mh_ctx* ctx);   /* GetIterationNumber (MultiH.h:
 /* stage timers mirroring the reference's printf timers (MultiH.cpp:68,74,258,310): ms for
  * [0] point-wise homographies [1] stable clusters [2] adjacency [3] alternating optimisation [4] total */
 mh_status mh_get_stage_ms(const mh_ctx* ctx, double ms[5]);
+
+/* ---- diagnostics (measurement aids, not part of the reference surface) -------- */
+/* FP32 FMA-pipe peak of this GPU: variant 0 = scalar FFMA, 1 = packed FFMA2; the roofline denominator of K2. */
+mh_status mh_diag_fp32_peak(mh_ctx* ctx, int32_t variant, int32_t iters, double* tflops_out, double* ms_out);
+/* K2 fused inner loop: 1 = packed FFMA2 (default), 0 = scalar FFMA (A/B evidence only). */
+mh_status mh_diag_set_fused_variant(mh_ctx* ctx, int32_t variant);
 
 #ifdef __cplusplus
 }

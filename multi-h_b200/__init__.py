@@ -11,7 +11,8 @@ This Python package is only the host-side binding used by tests and bench.py:
 """
 from . import scenes  # noqa: F401
 from . import capi  # noqa: F401
+from . import dist  # noqa: F401
 from .capi import Context, MHError, build_library, library_path  # noqa: F401
 from .multih import MultiH  # noqa: F401
 
-__all__ = ["capi", "scenes", "Context", "MHError", "MultiH", "build_library", "library_path"]
+__all__ = ["capi", "scenes", "dist", "Context", "MHError", "MultiH", "build_library", "library_path"]

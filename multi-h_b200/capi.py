@@ -26,8 +26,8 @@ SYMBOLS = [
     "mh_set_geometry", "mh_get_geometry", "mh_upload_correspondences", "mh_hypotheses_from_host",
     "mh_hypotheses_to_host", "mh_haf_hypotheses", "mh_data_cost_dense", "mh_residuals", "mh_data_cost_fused",
     "mh_inlier_stats", "mh_inliers_of_homography", "mh_features10", "mh_features6", "mh_meanshift", "mh_refit_haf",
-    "mh_refit_3pt", "mh_modes_to_hypotheses", "mh_neighbourhood", "mh_alpha_expansion", "mh_process", "mh_get_energy",
-    "mh_get_iterations", "mh_get_stage_ms",
+    "mh_refit_haf_accumulate", "mh_refit_haf_solve", "mh_refit_3pt", "mh_modes_to_hypotheses", "mh_neighbourhood", "mh_alpha_expansion", "mh_process", "mh_get_energy",
+    "mh_get_iterations", "mh_get_stage_ms", "mh_diag_fp32_peak", "mh_diag_set_fused_variant",
 ]
 
 
@@ -43,7 +43,7 @@ class Params(C.Structure):
         ("thr_fundamental", C.c_double), ("thr_homography", C.c_double), ("locality", C.c_double),
         ("lambda_", C.c_double), ("min_inliers", C.c_int32), ("straightness", C.c_double),
         ("max_iterations", C.c_int32), ("convergence", C.c_double), ("meanshift_metric", C.c_int32),
-        ("rng_seed", C.c_uint32), ("max_gc_cycles", C.c_int32),
+        ("rng_seed", C.c_uint32), ("max_gc_cycles", C.c_int32), ("max_neighbours", C.c_int32),
     ]
 
 
@@ -103,19 +103,19 @@ def _p(a, ct):
 
 
 # ---- host-only entry points (no GPU needed) --------------------------------------------------------------------------
-def neighbourhood(pts, radius):
-    """mh_neighbourhood: exact 4-D radius search replacing FlannBasedMatcher::radiusMatch (MultiH.cpp:231-253)."""
+def neighbourhood(pts, radius, max_neighbours=31):
+    """mh_neighbourhood: 4-D neighbourhood replacing FlannBasedMatcher::radiusMatch (MultiH.cpp:231-253)."""
     pts = _np(pts, np.float64)
     N = pts.shape[0]
     offsets = np.zeros(N + 1, dtype=np.int64)
     total = C.c_int64(0)
-    st = lib().mh_neighbourhood(None, _p(pts, C.c_double), N, C.c_double(radius), _p(offsets, C.c_int64), None,
-                                C.byref(total))
+    st = lib().mh_neighbourhood(None, _p(pts, C.c_double), N, C.c_double(radius), int(max_neighbours),
+                                _p(offsets, C.c_int64), None, C.byref(total))
     if st:
         raise MHError(st, "mh_neighbourhood")
     adj = np.zeros(max(total.value, 1), dtype=np.int32)
-    st = lib().mh_neighbourhood(None, _p(pts, C.c_double), N, C.c_double(radius), _p(offsets, C.c_int64),
-                                _p(adj, C.c_int32), C.byref(total))
+    st = lib().mh_neighbourhood(None, _p(pts, C.c_double), N, C.c_double(radius), int(max_neighbours),
+                                _p(offsets, C.c_int64), _p(adj, C.c_int32), C.byref(total))
     if st:
         raise MHError(st, "mh_neighbourhood")
     return offsets, adj[: total.value]
@@ -316,6 +316,16 @@ class Context:
                                        _vp(d_hyp), _vp(cnt)))
         return d_hyp, cnt[:K]
 
+    def refit_haf_accumulate(self, d_pts, d_aff, d_labels, K, out=None):
+        acc = out if out is not None else self._empty((K, 12), self.torch.float64)
+        self._check(lib().mh_refit_haf_accumulate(self._h, _vp(d_pts), _vp(d_aff), _vp(d_labels),
+                                                  C.c_int64(d_pts.shape[0]), int(K), _vp(acc)))
+        return acc
+
+    def refit_haf_solve(self, d_acc, d_hyp, d_count=None):
+        self._check(lib().mh_refit_haf_solve(self._h, _vp(d_acc), int(d_acc.shape[0]), _vp(d_hyp), _vp(d_count)))
+        return d_hyp
+
     def refit_3pt(self, d_pts, d_assign, Cn):
         t = self.torch
         d_hyp = t.zeros((max(Cn, 1), 12), dtype=t.float32, device=self.device)
@@ -340,6 +350,14 @@ class Context:
         self._check(lib().mh_process(self._h, _p(pts, C.c_double), _p(aff, C.c_double), _p(F, C.c_double), N,
                                      _p(labels, C.c_int32), _p(H, C.c_double), int(kmax), C.byref(K)))
         return labels, H[: K.value].copy(), int(K.value)
+
+    def fp32_peak(self, variant=1, iters=20000):
+        tf = C.c_double(0); ms = C.c_double(0)
+        self._check(lib().mh_diag_fp32_peak(self._h, int(variant), int(iters), C.byref(tf), C.byref(ms)))
+        return tf.value
+
+    def set_fused_variant(self, v):
+        self._check(lib().mh_diag_set_fused_variant(self._h, int(v)))
 
     @property
     def energy(self):

@@ -150,6 +150,7 @@ void mh_default_params(mh_params* p) {
   p->meanshift_metric = 0;
   p->rng_seed = 1u;
   p->max_gc_cycles = 1000;   // MultiH.cpp:543
+  p->max_neighbours = 31;    // FLANN default SearchParams: checks = 32 (query included)
 }
 
 mh_status mh_create(const mh_params* params, int device, mh_ctx** out) {
@@ -446,6 +447,20 @@ mh_status mh_refit_haf(mh_ctx* ctx, const void* d_pts, const void* d_aff, const 
   if (N < 0 || K < 0 || (N && (!d_pts || !d_aff || !d_labels)) || (K && !d_hyp)) return fail(ctx, MH_EINVAL, "mh_refit_haf: bad arguments");
   return launch_refit_haf(ctx, (const float4*)d_pts, (const float4*)d_aff, (const int32_t*)d_labels, N, K, (float*)d_hyp,
                           (int32_t*)d_count);
+}
+
+mh_status mh_refit_haf_accumulate(mh_ctx* ctx, const void* d_pts, const void* d_aff, const void* d_labels, int64_t N,
+                                  int32_t K, void* d_acc) {
+  NEED_GEOM(ctx);
+  if (N < 0 || K < 0 || (N && (!d_pts || !d_aff || !d_labels)) || (K && !d_acc)) return fail(ctx, MH_EINVAL, "mh_refit_haf_accumulate: bad arguments");
+  return launch_refit_haf_accumulate(ctx, (const float4*)d_pts, (const float4*)d_aff, (const int32_t*)d_labels, N, K,
+                                     (double*)d_acc);
+}
+
+mh_status mh_refit_haf_solve(mh_ctx* ctx, const void* d_acc, int32_t K, void* d_hyp, void* d_count) {
+  NEED_GEOM(ctx);
+  if (K < 0 || (K && (!d_acc || !d_hyp))) return fail(ctx, MH_EINVAL, "mh_refit_haf_solve: bad arguments");
+  return launch_refit_haf_solve(ctx, (const double*)d_acc, K, (float*)d_hyp, (int32_t*)d_count);
 }
 
 mh_status mh_refit_3pt(mh_ctx* ctx, const void* d_pts, const void* d_assign, int64_t N, int32_t C, void* d_hyp,

@@ -113,6 +113,9 @@ mh_status launch_meanshift(mh_ctx*, const double* d_feat, int N, int D, double b
                            double* d_centres, int max_c, int32_t* d_assign, int* C_out, int64_t* stats);
 mh_status launch_refit_haf(mh_ctx*, const float4* d_pts, const float4* d_aff, const int32_t* d_labels, int64_t N, int K,
                            float* d_hyp, int32_t* d_count);
+mh_status launch_refit_haf_accumulate(mh_ctx*, const float4* d_pts, const float4* d_aff, const int32_t* d_labels,
+                                      int64_t N, int K, double* d_acc);
+mh_status launch_refit_haf_solve(mh_ctx*, const double* d_acc, int K, float* d_hyp, int32_t* d_count);
 mh_status launch_refit_3pt(mh_ctx*, const float4* d_pts, const int32_t* d_assign, int64_t N, int C, float* d_hyp,
                            int32_t* d_keep);
 mh_status launch_modes_to_hyp(mh_ctx*, const double* d_modes, int C, float* d_hyp);

@@ -1,6 +1,6 @@
 // ============================================================================
 // host_graphcut.cpp — host-side combinatorial steps that consume the GPU-built
-// data costs: exact 4-D radius neighbourhood and alpha-expansion.
+// data costs: 4-D neighbourhood and alpha-expansion.
 //
 // Own implementation (nothing is taken from the reference's vendored GCO /
 // maxflow sources, whose licence forbids redistribution).  It plays the role of
@@ -257,12 +257,16 @@ mh_status alpha_expansion(const int32_t* cost, int N, int L, int potts, const in
 }
 
 // ---------------------------------------------------------------------------
-// Exact radius neighbourhood on float (x1,y1,x2,y2): d^2 <= radius^2 (OpenCV's
-// FlannBasedMatcher squares maxDistance for the L2 index).  Uniform grid over
-// (x1,y1) with cell = radius.  Neighbours of a site are listed in ascending
-// index order; the site itself is excluded (MultiH.cpp:537).
+// Neighbourhood on float (x1,y1,x2,y2): the `max_neighbours` nearest sites (ties by index) among those with
+// d^2 <= radius^2 (OpenCV's FlannBasedMatcher squares maxDistance for the L2 index); max_neighbours <= 0 = the full
+// ball.  This restates what the reference's radiusMatch call returns with FLANN's default parameters (4 randomised
+// KD-trees, checks = 32, radius result set always "full" => the search stops after 32 examined points, the query
+// among them) as an exactly defined set — see oracle/multih_oracle.cpp orc_radius_neighbours.
+// Uniform grid over (x1,y1), ring search with early termination.  Neighbours are listed in ascending index order;
+// the site itself is excluded (MultiH.cpp:537).
 // ---------------------------------------------------------------------------
-int64_t radius_neighbourhood(const double* pts, int N, double radius, int64_t* offsets, int32_t* adj) {
+int64_t radius_neighbourhood(const double* pts, int N, double radius, int max_neighbours, int64_t* offsets,
+                             int32_t* adj) {
   if (N <= 0) { if (offsets) offsets[0] = 0; return 0; }
   const float r = (float)radius, r2 = r * r;
   float minx = 1e30f, miny = 1e30f, maxx = -1e30f, maxy = -1e30f;
@@ -272,41 +276,79 @@ int64_t radius_neighbourhood(const double* pts, int N, double radius, int64_t* o
     minx = std::min(minx, p[4 * (size_t)i]); maxx = std::max(maxx, p[4 * (size_t)i]);
     miny = std::min(miny, p[4 * (size_t)i + 1]); maxy = std::max(maxy, p[4 * (size_t)i + 1]);
   }
-  const float cell = std::max(r, 1e-6f);
+  const bool knn = max_neighbours > 0;
+  // cell size: the radius for ball queries; ~4 sites per cell for k-nearest queries (never above the radius)
+  float cell = std::max(r, 1e-6f);
+  if (knn) {
+    const double area = std::max(1e-12, (double)(maxx - minx) * (double)(maxy - miny));
+    cell = std::min(cell, (float)std::sqrt(area * 4.0 / N));
+    cell = std::max(cell, 1e-6f);
+  }
   const int gx = std::max(1, std::min(4096, (int)((maxx - minx) / cell) + 1));
   const int gy = std::max(1, std::min(4096, (int)((maxy - miny) / cell) + 1));
-  auto cx = [&](float x) { return std::min(gx - 1, std::max(0, (int)((x - minx) / cell))); };
-  auto cy = [&](float y) { return std::min(gy - 1, std::max(0, (int)((y - miny) / cell))); };
+  const float cw = std::max(cell, (maxx - minx) / gx + 1e-6f), ch = std::max(cell, (maxy - miny) / gy + 1e-6f);
+  auto cx = [&](float x) { return std::min(gx - 1, std::max(0, (int)((x - minx) / cw))); };
+  auto cy = [&](float y) { return std::min(gy - 1, std::max(0, (int)((y - miny) / ch))); };
+  const float cmin = std::min(cw, ch);
   std::vector<int> cstart((size_t)gx * gy + 1, 0), order(N);
   for (int i = 0; i < N; ++i) ++cstart[(size_t)cy(p[4 * (size_t)i + 1]) * gx + cx(p[4 * (size_t)i]) + 1];
   for (size_t c = 0; c < (size_t)gx * gy; ++c) cstart[c + 1] += cstart[c];
   {
     std::vector<int> cur(cstart.begin(), cstart.end() - 1);
-    for (int i = 0; i < N; ++i) order[cur[(size_t)cy(p[4 * (size_t)i + 1]) * gx + cx(p[4 * (size_t)i])]++] = i;  // ascending index per cell
+    for (int i = 0; i < N; ++i) order[cur[(size_t)cy(p[4 * (size_t)i + 1]) * gx + cx(p[4 * (size_t)i])]++] = i;
   }
   int64_t total = 0;
+  typedef std::pair<float, int> Cand;
+  std::vector<Cand> heap;  // max-heap on (d2, index): top = worst kept candidate
   std::vector<int32_t> row;
+  const int max_ring = std::max(gx, gy);
   for (int i = 0; i < N; ++i) {
     if (offsets) offsets[i] = total;
     const float* a = &p[4 * (size_t)i];
     const int ix = cx(a[0]), iy = cy(a[1]);
-    row.clear();
-    for (int yy = std::max(0, iy - 1); yy <= std::min(gy - 1, iy + 1); ++yy)
-      for (int xx = std::max(0, ix - 1); xx <= std::min(gx - 1, ix + 1); ++xx) {
+    heap.clear();
+    for (int ring = 0; ring <= max_ring; ++ring) {
+      if (ring > 0) {
+        const float reach = (ring - 1) * cmin;  // every site of this ring is at least this far away in (x1,y1)
+        if (reach * reach > r2) break;
+        if (knn && (int)heap.size() == max_neighbours && reach * reach > heap.front().first) break;
+      }
+      if (ring > std::max(std::max(ix, gx - 1 - ix), std::max(iy, gy - 1 - iy))) break;  // past the grid
+      const int y0 = iy - ring, y1 = iy + ring, x0 = ix - ring, x1 = ix + ring;
+      auto visit = [&](int xx, int yy) {
+        if (xx < 0 || yy < 0 || xx >= gx || yy >= gy) return;
         const size_t c = (size_t)yy * gx + xx;
         for (int k = cstart[c]; k < cstart[c + 1]; ++k) {
           const int j = order[k];
           if (j == i) continue;
           const float* b = &p[4 * (size_t)j];
           const float d0 = a[0] - b[0], d1 = a[1] - b[1], d2 = a[2] - b[2], d3 = a[3] - b[3];
-          if (d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3 <= r2) row.push_back(j);
+          const float d = d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
+          if (d > r2) continue;
+          const Cand cand(d, j);
+          if (!knn || (int)heap.size() < max_neighbours) {
+            heap.push_back(cand);
+            if (knn) std::push_heap(heap.begin(), heap.end());
+          } else if (cand < heap.front()) {
+            std::pop_heap(heap.begin(), heap.end());
+            heap.back() = cand;
+            std::push_heap(heap.begin(), heap.end());
+          }
         }
+      };
+      if (ring == 0) visit(ix, iy);
+      else {
+        for (int xx = x0; xx <= x1; ++xx) { visit(xx, y0); visit(xx, y1); }
+        for (int yy = y0 + 1; yy <= y1 - 1; ++yy) { visit(x0, yy); visit(x1, yy); }
       }
+    }
     if (adj) {
+      row.clear();
+      for (const Cand& c : heap) row.push_back(c.second);
       std::sort(row.begin(), row.end());
       std::memcpy(adj + total, row.data(), sizeof(int32_t) * row.size());
     }
-    total += (int64_t)row.size();
+    total += (int64_t)heap.size();
   }
   if (offsets) offsets[N] = total;
   return total;

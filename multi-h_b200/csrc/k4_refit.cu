@@ -181,15 +181,22 @@ __global__ void __launch_bounds__(256) haf_segment_accumulate_kernel(const float
 }
 
 // ---- 5a: batched 4x4 eigen-solves ------------------------------------------------
-__global__ void haf_solve_kernel(const double* __restrict__ acc, const int32_t* __restrict__ count, int K,
-                                 float* __restrict__ hyp, int32_t* __restrict__ count_out, HafGeom g) {
+// acc layout per label: 10 uniques of SUM A^T A (row-major upper triangle), [10] = member count, [11] = pad — one
+// (K,12) FP64 array so that a single all-reduce(sum) combines the partial statistics of correspondence shards.
+__global__ void acc_count_kernel(const int32_t* __restrict__ count, int K, double* __restrict__ acc) {
+  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  if (l < K) { acc[12 * (size_t)l + 10] = (double)count[l]; acc[12 * (size_t)l + 11] = 0.0; }
+}
+
+__global__ void haf_solve_kernel(const double* __restrict__ acc, int K, float* __restrict__ hyp,
+                                 int32_t* __restrict__ count_out, HafGeom g) {
   const int l = blockIdx.x * blockDim.x + threadIdx.x;
   if (l >= K) return;
-  const int n = count[l];
+  const double* a = acc + 12 * (size_t)l;
+  const int n = (int)(a[10] + 0.5);
   if (count_out) count_out[l] = n;
   if (n == 0) return;  // MultiH.cpp:592-593: label without members keeps its homography
   double M[4][4];
-  const double* a = acc + 12 * (size_t)l;
   int q = 0;
 #pragma unroll
   for (int r = 0; r < 4; ++r)
@@ -200,21 +207,38 @@ __global__ void haf_solve_kernel(const double* __restrict__ acc, const int32_t* 
   haf_store(v, g, false, hyp + 12 * (size_t)l);  // no division by h33 (MultiH.cpp:977-989)
 }
 
-mh_status launch_refit_haf(mh_ctx* ctx, const float4* d_pts, const float4* d_aff, const int32_t* d_labels, int64_t N,
-                           int K, float* d_hyp, int32_t* d_count) {
+mh_status launch_refit_haf_accumulate(mh_ctx* ctx, const float4* d_pts, const float4* d_aff, const int32_t* d_labels,
+                                      int64_t N, int K, double* d_acc) {
   if (K <= 0) return MH_OK;
   if (N > 0x7fffffff) return fail(ctx, MH_EINVAL, "mh_refit_haf: N must fit int32");
   Csr c;
   MH_TRY(build_csr(ctx, d_labels, N, K, c));
+  MH_CUDA(ctx, cudaMemsetAsync(d_acc, 0, sizeof(double) * 12 * (size_t)K, ctx->stream));
   const HafGeom g = haf_geom(ctx);
   if (N > 0) {
     haf_segment_accumulate_kernel<<<(unsigned)((N + 255) / 256), 256, 0, ctx->stream>>>(d_pts, d_aff, c.members,
-                                                                                        c.sorted_label, c.offsets, K, c.acc, g);
+                                                                                        c.sorted_label, c.offsets, K, d_acc, g);
     MH_LAUNCHED(ctx, "haf_segment_accumulate_kernel");
   }
-  haf_solve_kernel<<<(unsigned)((K + 63) / 64), 64, 0, ctx->stream>>>(c.acc, c.count, K, d_hyp, d_count, g);
+  acc_count_kernel<<<(unsigned)((K + 255) / 256), 256, 0, ctx->stream>>>(c.count, K, d_acc);
+  MH_LAUNCHED(ctx, "acc_count_kernel");
+  return MH_OK;
+}
+
+mh_status launch_refit_haf_solve(mh_ctx* ctx, const double* d_acc, int K, float* d_hyp, int32_t* d_count) {
+  if (K <= 0) return MH_OK;
+  haf_solve_kernel<<<(unsigned)((K + 63) / 64), 64, 0, ctx->stream>>>(d_acc, K, d_hyp, d_count, haf_geom(ctx));
   MH_LAUNCHED(ctx, "haf_solve_kernel");
   return MH_OK;
+}
+
+mh_status launch_refit_haf(mh_ctx* ctx, const float4* d_pts, const float4* d_aff, const int32_t* d_labels, int64_t N,
+                           int K, float* d_hyp, int32_t* d_count) {
+  if (K <= 0) return MH_OK;
+  MH_TRY(ensure_staging(ctx, sizeof(double) * 12 * (uint64_t)K));
+  double* acc = (double*)ctx->staging;
+  MH_TRY(launch_refit_haf_accumulate(ctx, d_pts, d_aff, d_labels, N, K, acc));
+  return launch_refit_haf_solve(ctx, acc, K, d_hyp, d_count);
 }
 
 // ---- 3PT -------------------------------------------------------------------------

@@ -21,7 +21,7 @@
 namespace mh {
 mh_status alpha_expansion(const int32_t* cost, int N, int L, int potts, const int64_t* offsets, const int32_t* adj,
                           const int32_t* init, int max_cycles, int32_t* lab, int64_t* energy_out);
-int64_t radius_neighbourhood(const double* pts, int N, double radius, int64_t* offsets, int32_t* adj);
+int64_t radius_neighbourhood(const double* pts, int N, double radius, int max_neighbours, int64_t* offsets, int32_t* adj);
 }  // namespace mh
 
 using namespace mh;
@@ -46,11 +46,11 @@ double now_ms() {
 
 extern "C" {
 
-mh_status mh_neighbourhood(mh_ctx* ctx, const double* pts, int32_t N, double radius, int64_t* offsets, int32_t* adj,
-                           int64_t* total_out) {
+mh_status mh_neighbourhood(mh_ctx* ctx, const double* pts, int32_t N, double radius, int32_t max_neighbours,
+                           int64_t* offsets, int32_t* adj, int64_t* total_out) {
   // host-only: ctx may be NULL
   if (N < 0 || (N && !pts) || !(radius >= 0)) return ctx ? fail(ctx, MH_EINVAL, "mh_neighbourhood: bad arguments") : MH_EINVAL;
-  const int64_t t = radius_neighbourhood(pts, N, radius, offsets, adj);
+  const int64_t t = radius_neighbourhood(pts, N, radius, max_neighbours, offsets, adj);
   if (total_out) *total_out = t;
   return MH_OK;
 }
@@ -113,9 +113,9 @@ mh_status mh_process(mh_ctx* ctx, const double* pts, const double* aff, const do
   t0 = now_ms();
   std::vector<int64_t> offsets((size_t)N + 1);
   int64_t total = 0;
-  MH_TRY(mh_neighbourhood(ctx, pts, N, 1.0 / P.locality, offsets.data(), nullptr, &total));
+  MH_TRY(mh_neighbourhood(ctx, pts, N, 1.0 / P.locality, P.max_neighbours, offsets.data(), nullptr, &total));
   std::vector<int32_t> adj((size_t)std::max<int64_t>(total, 1));
-  MH_TRY(mh_neighbourhood(ctx, pts, N, 1.0 / P.locality, offsets.data(), adj.data(), &total));
+  MH_TRY(mh_neighbourhood(ctx, pts, N, 1.0 / P.locality, P.max_neighbours, offsets.data(), adj.data(), &total));
   ctx->stage_ms[2] = now_ms() - t0;
 
   // ---- alternating optimisation (MultiH.cpp:260-311) ------------------------------------

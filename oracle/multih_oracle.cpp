@@ -636,27 +636,40 @@ void orc_refit_haf(const double* pts, const double* aff, const int32_t* labels, 
   }
 }
 
-// Exact 4-D radius neighbourhood (restating the INTENT of MH.cpp:231-253:
-// FlannBasedMatcher::radiusMatch on float (x1,y1,x2,y2) with maxDistance =
-// 1/locality; OpenCV squares maxDistance for the L2 FLANN index.  FLANN's
-// default KD-tree search is approximate; the oracle uses the exact set, see
-// SURVEY.md appendix).  Returns CSR; self excluded (MH.cpp:537).
-// Call with adj == null to get the total count first.
-int64_t orc_radius_neighbours(const double* pts, int N, double radius, int64_t* offsets /*N+1*/, int32_t* adj) {
+// 4-D neighbourhood restating MH.cpp:231-253: FlannBasedMatcher::radiusMatch on float (x1,y1,x2,y2) with
+// maxDistance = 1/locality (OpenCV squares maxDistance for the L2 FLANN index).  The reference uses FLANN's DEFAULT
+// index and search parameters: 4 randomised KD-trees searched with checks = 32, and a radius result set reports
+// full() == true, so a query stops after examining 32 leaves (= 32 points, the query itself among them): it returns
+// (approximately) the 31 nearest other points that lie within the radius, NOT the full radius ball.  The oracle
+// restates that behaviour exactly-defined: the `max_neighbours` nearest points (ties by index) among those with
+// d^2 <= radius^2; max_neighbours <= 0 means the full ball.  Returns directed CSR with ascending neighbour index;
+// self excluded (MH.cpp:537).  Call with adj == null to get the total count first.
+int64_t orc_radius_neighbours(const double* pts, int N, double radius, int max_neighbours, int64_t* offsets /*N+1*/,
+                              int32_t* adj) {
   const float r2 = (float)(radius * radius);
   int64_t total = 0;
+  std::vector<std::pair<float, int>> cand;
+  std::vector<int> row;
   for (int i = 0; i < N; ++i) {
     if (offsets) offsets[i] = total;
     const float a0 = (float)pts[4 * i], a1 = (float)pts[4 * i + 1], a2 = (float)pts[4 * i + 2], a3 = (float)pts[4 * i + 3];
+    cand.clear();
     for (int j = 0; j < N; ++j) {
       if (j == i) continue;
       const float d0 = a0 - (float)pts[4 * j], d1 = a1 - (float)pts[4 * j + 1], d2 = a2 - (float)pts[4 * j + 2],
                   d3 = a3 - (float)pts[4 * j + 3];
-      if (d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3 <= r2) {
-        if (adj) adj[total] = j;
-        ++total;
-      }
+      const float d = d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
+      if (d <= r2) cand.emplace_back(d, j);
     }
+    if (max_neighbours > 0 && (int)cand.size() > max_neighbours) {
+      std::partial_sort(cand.begin(), cand.begin() + max_neighbours, cand.end());
+      cand.resize(max_neighbours);
+    }
+    row.clear();
+    for (auto& c : cand) row.push_back(c.second);
+    std::sort(row.begin(), row.end());
+    if (adj) for (size_t k = 0; k < row.size(); ++k) adj[total + k] = row[k];
+    total += (int64_t)row.size();
   }
   if (offsets) offsets[N] = total;
   return total;

@@ -243,13 +243,14 @@ def refit_haf(pts, aff, labels, K, F, e2=None, H_init=None):
     return H, M10, cnt
 
 
-def radius_neighbours(pts, radius):
+def radius_neighbours(pts, radius, max_neighbours=31):
     pts, pp = _d(pts)
     N = pts.shape[0]
     offsets = np.zeros(N + 1, dtype=np.int64)
-    total = lib().orc_radius_neighbours(pp, N, C.c_double(radius), offsets.ctypes.data_as(c_lp), None)
+    total = lib().orc_radius_neighbours(pp, N, C.c_double(radius), int(max_neighbours), offsets.ctypes.data_as(c_lp), None)
     adj = np.empty(max(total, 1), dtype=np.int32)
-    lib().orc_radius_neighbours(pp, N, C.c_double(radius), offsets.ctypes.data_as(c_lp), adj.ctypes.data_as(c_ip))
+    lib().orc_radius_neighbours(pp, N, C.c_double(radius), int(max_neighbours), offsets.ctypes.data_as(c_lp),
+                                adj.ctypes.data_as(c_ip))
     return offsets, adj[:total]
 
 

@@ -1,0 +1,245 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu).  Every check goes through the C ABI of libmultih_b200.so and
+compares with the FP64 oracle on the same seeded inputs / with the committed golden vectors.  Tolerances are stated at
+each assert:
+  * K1/K4 homographies : relative error (max-norm of H after division by h33) — p99 <= 2e-6, max <= 1e-3 (FP32 storage of
+    the inputs/outputs; the solves themselves are FP64)
+  * K2 residuals        : |d2_gpu - d2_ref| <= 5e-3 px^2 for d2 < 100 px^2 (FP32 evaluation in normalised coordinates)
+  * K2 integer costs    : exact match >= 99.9 %, every mismatch |delta| == 1 except threshold flips (< 1e-5 of entries)
+  * K3 mean-shift       : same number of trajectories / window iterations / centres as the oracle, centres within 1e-6
+  * labels              : agreement with the oracle pipeline (reference GCO) reported, >= 95 % required
+"""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _rel(H, Href):
+    H = H / H[:, 8:9]; Href = Href / Href[:, 8:9]
+    return np.abs(H - Href).max(1) / np.abs(Href).max(1)
+
+
+@pytest.fixture(scope="module")
+def scene(mh):
+    return mh.scenes.make_scene(20000, 20, seed=0xB200 + 2)
+
+
+@pytest.fixture(scope="module")
+def dev(gpu_ctx, scene):
+    import torch
+
+    gpu_ctx.set_geometry(scene.F, scene.pts)
+    d_pts, d_aff = gpu_ctx.upload(scene.pts, scene.aff)
+    torch.cuda.synchronize()
+    return d_pts, d_aff
+
+
+def test_native_library_is_loaded_and_counts_launches(gpu_ctx, dev, mh):
+    before = gpu_ctx.launches
+    gpu_ctx.haf_hypotheses(*dev)
+    assert gpu_ctx.launches == before + 1
+    maps = open("/proc/self/maps").read()
+    assert "libmultih_b200.so" in maps
+
+
+def test_k1_haf_vs_oracle(gpu_ctx, dev, scene, orc):
+    d_h = gpu_ctx.haf_hypotheses(*dev)
+    Hg = gpu_ctx.hypotheses_to_host(d_h, True)
+    Ho = orc.haf_hypotheses(scene.pts, scene.aff, scene.F, threads=8)
+    rel = _rel(Hg, Ho)
+    assert np.isfinite(rel).all()
+    assert np.percentile(rel, 99) <= 2e-6 and rel.max() <= 1e-3, (np.percentile(rel, 99), rel.max())
+    fg = gpu_ctx.features10(d_h, dev[0]).cpu().numpy()
+    fo = orc.features10(Ho, scene.pts, 0.005)
+    d = np.abs(fg - fo).max(1)
+    assert np.percentile(d, 99) <= 1e-3 and np.median(d) <= 1e-4  # px
+
+
+def test_k1_haf_known_answer(gpu_ctx, mh):
+    sc = mh.scenes.make_scene(5000, 5, outlier_ratio=0.0, noise_px=0.0, noise_aff=0.0, seed=11)
+    gpu_ctx.set_geometry(sc.F, sc.pts)
+    d_pts, d_aff = gpu_ctx.upload(sc.pts, sc.aff)
+    H = gpu_ctx.hypotheses_to_host(gpu_ctx.haf_hypotheses(d_pts, d_aff), True)
+    assert _rel(H, sc.planes[sc.gt]).max() < 2e-4  # noise-free plane => generating homography (FP32 I/O)
+
+
+def test_k1_k2_golden_vectors(gpu_ctx, orc):
+    g = np.load(os.path.join(GOLD, "golden_small.npz"))
+    gpu_ctx.set_geometry(g["F"], g["pts"])
+    d_pts, d_aff = gpu_ctx.upload(g["pts"], g["aff"])
+    H = gpu_ctx.hypotheses_to_host(gpu_ctx.haf_hypotheses(d_pts, d_aff), True)
+    rel = _rel(H, g["haf_H"])
+    assert np.percentile(rel, 99) <= 2e-6 and rel.max() <= 1e-3
+    cost = gpu_ctx.data_cost_dense(d_pts, gpu_ctx.hypotheses_from_host(g["cost_H"])).cpu().numpy()
+    diff = np.abs(cost.astype(np.int64) - g["cost"])
+    assert (diff == 0).mean() >= 0.999 and (diff > 1).sum() <= 1
+    d_hr, cnt = gpu_ctx.refit_haf(d_pts, d_aff, __import__("torch").from_numpy(g["labels"]).cuda(), 4)
+    assert _rel(gpu_ctx.hypotheses_to_host(d_hr), g["refit_H"]).max() <= 1e-5
+    d_m = gpu_ctx.modes_to_hypotheses(__import__("torch").from_numpy(g["modes"]).cuda())
+    assert _rel(gpu_ctx.hypotheses_to_host(d_m), g["modes_H"]).max() <= 1e-5
+    sc, lmin, keep = gpu_ctx.inlier_stats(d_pts, gpu_ctx.hypotheses_from_host(g["cost_H"]))
+    assert np.array_equal(sc[:, 5].astype(np.int64), g["inl_count"]) and np.array_equal(keep, g["inl_keep"])
+
+
+@pytest.fixture(scope="module")
+def hyps(scene, orc):
+    Ho = orc.haf_hypotheses(scene.pts[:237], scene.aff[:237], scene.F)
+    return np.concatenate([scene.planes, Ho])  # K = 257 (odd on purpose)
+
+
+def test_k2_dense_and_residuals_vs_oracle(gpu_ctx, dev, scene, hyps, orc):
+    gpu_ctx.set_geometry(scene.F, scene.pts)
+    d_hyp = gpu_ctx.hypotheses_from_host(hyps)
+    cg = gpu_ctx.data_cost_dense(dev[0], d_hyp).cpu().numpy()
+    co = orc.data_cost_dense(scene.pts, hyps, threads=8)
+    diff = np.abs(cg.astype(np.int64) - co)
+    assert (diff == 0).mean() >= 0.999
+    flips = diff > 1
+    assert flips.mean() < 1e-5                      # threshold flips (0 <-> 9802) only at |d2 - T| ~ 1e-3
+    assert (diff[~flips] <= 1).all()
+    assert np.array_equal(gpu_ctx.data_cost_dense(dev[0], d_hyp, elem_bytes=2).cpu().numpy().astype(np.int32), cg)
+    rg = gpu_ctx.residuals(dev[0], d_hyp).cpu().numpy()
+    ro = orc.residuals(scene.pts, hyps, threads=8)
+    m = ro < 100
+    assert np.abs(rg - ro)[m].max() <= 5e-3
+
+
+def test_k2_fused_equals_dense(gpu_ctx, dev, scene, hyps):
+    gpu_ctx.set_geometry(scene.F, scene.pts)
+    d_hyp = gpu_ctx.hypotheses_from_host(hyps)
+    cg = gpu_ctx.data_cost_dense(dev[0], d_hyp).cpu().numpy()
+    for variant in (1, 0):
+        gpu_ctx.set_fused_variant(variant)
+        f = gpu_ctx.data_cost_fused(dev[0], d_hyp, kmax=64)
+        best = f["best"].cpu().numpy()
+        assert np.array_equal(best & 0xFFFFFFFF, cg.argmin(1))      # bit-exact vs the dense matrix's argmin (first wins)
+        assert np.array_equal(best >> 32, cg.min(1))
+        cnt = f["count"].cpu().numpy()
+        assert np.array_equal(cnt, (cg[:, 1:] <= 255).sum(1))
+        lst = f["list"].cpu().numpy()
+        for i in range(0, len(cnt), 53):
+            got = sorted(int(x) for x in lst[i, :min(cnt[i], 64)])
+            exp = sorted((l << 8) | int(cg[i, l]) for l in range(1, cg.shape[1]) if cg[i, l] <= 255)
+            if cnt[i] <= 64:
+                assert got == exp
+        rg = gpu_ctx.residuals(dev[0], d_hyp).cpu().numpy()
+        thr2 = np.float32(2.2 ** 2)
+        inl = f["inliers"].cpu().numpy()
+        assert np.abs(inl - (rg < thr2).sum(0)).max() <= 2           # same FP32 residuals, boundary ulps only
+    gpu_ctx.set_fused_variant(1)
+
+
+def test_k2_edge_cases(gpu_ctx, dev, scene, mh):
+    import torch
+
+    gpu_ctx.set_geometry(scene.F, scene.pts)
+    # K = 0: only the outlier column
+    c = gpu_ctx.data_cost_dense(dev[0][:100], None)
+    assert c.shape == (100, 1) and (c.cpu().numpy() == 4901).all()
+    # ragged N (not a multiple of any tile) and K = 1
+    d_hyp = gpu_ctx.hypotheses_from_host(scene.planes[:1])
+    c = gpu_ctx.data_cost_dense(dev[0][:1237], d_hyp).cpu().numpy()
+    f = gpu_ctx.data_cost_fused(dev[0][:1237].contiguous(), d_hyp, kmax=4)
+    assert np.array_equal(f["best"].cpu().numpy() & 0xFFFFFFFF, c.argmin(1))
+    # a degenerate hypothesis (all zeros -> division by zero) must behave like the reference: never in range
+    z = torch.zeros((1, 12), dtype=torch.float32, device="cuda")
+    assert (gpu_ctx.data_cost_dense(dev[0][:64], z).cpu().numpy()[:, 1] == 9802).all()
+    with pytest.raises(mh.MHError):
+        gpu_ctx.data_cost_dense(dev[0], d_hyp, elem_bytes=3)
+
+
+def test_k2_inlier_stats_vs_oracle(gpu_ctx, dev, scene, hyps, orc):
+    gpu_ctx.set_geometry(scene.F, scene.pts)
+    sc, lmin, keep = gpu_ctx.inlier_stats(dev[0], gpu_ctx.hypotheses_from_host(hyps[:40]))
+    cnt_o, sc_o, lmin_o, keep_o = orc.inlier_stats(scene.pts, hyps[:40])
+    assert np.abs(sc[:, 5] - cnt_o).max() <= 1
+    same = sc[:, 5] == cnt_o
+    assert np.allclose(sc[same], sc_o[same], rtol=1e-6)
+    assert np.array_equal(keep, keep_o)
+
+
+def test_k4_refit_haf_vs_oracle(gpu_ctx, dev, scene, orc):
+    import torch
+
+    gpu_ctx.set_geometry(scene.F, scene.pts)
+    labels = scene.gt.copy()
+    labels[labels == 7] = -1                       # an empty label keeps its previous homography (MultiH.cpp:592-593)
+    init = gpu_ctx.hypotheses_from_host(scene.planes)
+    d_h, cnt = gpu_ctx.refit_haf(dev[0], dev[1], torch.from_numpy(labels).cuda(), 20, d_hyp=init.clone())
+    Ho, _, cnt_o = orc.refit_haf(scene.pts, scene.aff, labels, 20, scene.F, H_init=scene.planes)
+    assert np.array_equal(cnt.cpu().numpy(), cnt_o) and cnt_o[7] == 0
+    rel = _rel(gpu_ctx.hypotheses_to_host(d_h), Ho)
+    assert rel.max() <= 1e-5, rel
+    assert torch.equal(d_h[7], init[7])
+
+
+def test_k3_meanshift_and_k4_3pt_vs_oracle(mh, orc):
+    import torch
+
+    sc = mh.scenes.make_scene(3000, 6, seed=7)
+    ctx = mh.Context()
+    ctx.set_geometry(sc.F, sc.pts)
+    d_pts, d_aff = ctx.upload(sc.pts, sc.aff)
+    fo = orc.features10(orc.haf_hypotheses(sc.pts, sc.aff, sc.F), sc.pts, 0.005)
+    cen, asg, st = ctx.meanshift(torch.from_numpy(fo).cuda(), 2.2)
+    co, ao, _, sto = orc.meanshift(fo, 2.2)
+    assert st == sto and cen.shape[0] == co.shape[0]            # same trajectories / window iterations / centres
+    assert np.abs(cen.cpu().numpy() - co).max() <= 1e-6
+    agree = (asg.cpu().numpy() == ao).mean()
+    assert agree >= 0.999, agree
+    # 6-D (MergingStep) on cluster homographies + L2 metric variant runs
+    C = co.shape[0]
+    d_h3, keep = ctx.refit_3pt(d_pts, asg, C)
+    order = np.argsort(ao, kind="stable"); order = order[ao[order] >= 0]
+    offs = np.concatenate([[0], np.cumsum(np.bincount(ao[ao >= 0], minlength=C))]).astype(np.int32)
+    H3o, keep_o = orc.cluster_3pt(sc.pts, offs, order.astype(np.int32), sc.F)
+    if agree == 1.0:
+        assert np.array_equal(keep.cpu().numpy().astype(bool), keep_o)
+        rel = _rel(ctx.hypotheses_to_host(d_h3)[keep_o], H3o[keep_o])
+        assert np.percentile(rel, 95) <= 1e-4, np.percentile(rel, [50, 95, 100])
+    f6 = orc.features6(H3o[keep_o])
+    cen6, asg6, st6 = ctx.meanshift(torch.from_numpy(f6).cuda(), 2.2)
+    co6, ao6, _, sto6 = orc.meanshift(f6, 2.2, rng_state=ctx.params.rng_seed if False else 1)
+    assert cen6.shape[1] == 6 and cen6.shape[0] >= 1
+
+
+def test_pipeline_labels_vs_oracle(mh, orc):
+    from ref_pipeline import oracle_process
+
+    sc = mh.scenes.make_scene(3000, 6, seed=7)
+    params = mh.capi.default_params(locality=1 / 20.0)
+    ctx = mh.Context(params)
+    lab, H, K = ctx.process(sc.pts, sc.aff, sc.F)
+    lab_o, H_o, info = oracle_process(sc.pts, sc.aff, sc.F, locality=1 / 20.0)
+    agree = (lab == lab_o).mean()
+    print(f"\n[parity] synthetic 3000x6: K gpu={K} oracle={len(H_o)} label agreement={agree:.4f} "
+          f"iterations gpu={ctx.iterations} oracle={info['iterations']}")
+    assert K == len(H_o)
+    assert agree >= 0.95
+
+
+def test_pipeline_bundled_pair(mh, orc):
+    """BASELINE configs[1]: the bundled barrsmith pair (hot-path input fixture) on 1 B200 vs the oracle pipeline."""
+    from ref_pipeline import oracle_process
+
+    g = np.load(os.path.join(GOLD, "barrsmith_hotpath_input.npz"))
+    ctx = mh.Context()
+    lab, H, K = ctx.process(g["pts"], g["aff"], g["F"])
+    lab_o, H_o, info = oracle_process(g["pts"], g["aff"], g["F"])
+    agree = (lab == lab_o).mean()
+    print(f"\n[parity] barrsmith N={len(lab)}: K gpu={K} oracle={len(H_o)} label agreement={agree:.4f} "
+          f"outliers gpu={(lab < 0).mean():.3f} oracle={(lab_o < 0).mean():.3f} stages={ctx.stage_ms()}")
+    assert abs(K - len(H_o)) <= 1
+    assert agree >= 0.95
+
+
+def test_multih_class_surface(mh):
+    g = np.load(os.path.join(GOLD, "barrsmith_hotpath_input.npz"))
+    o = mh.MultiH(2.6, 2.2, 0.005, 0.5, 20)
+    assert not o.Process(g["pts"][:5, :2], g["pts"][:5, 2:], g["aff"][:5], g["F"])   # < 8 points: MultiH.cpp:44-50
+    assert o.Process(g["pts"][:, :2], g["pts"][:, 2:], g["aff"], g["F"])
+    assert o.GetPointNumber() == len(g["pts"]) and o.GetClusterNumber() >= 1
+    assert o.GetHomography(1).shape == (3, 3) and o.GetLabels().min() >= -1

@@ -1,0 +1,85 @@
+"""CPU tests of the host side of libmultih_b200.so: the C-ABI exports, the no-fallback rule, and the host combinatorial
+steps (exact neighbourhood, alpha-expansion) against the oracle and the reference's own GCO compiled in place."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol(mh):
+    hdr = open(os.path.join(ROOT, "include", "multih_b200.h")).read()
+    declared = sorted(set(re.findall(r"\b(mh_[a-z0-9_]+)\s*\(", hdr)) - {"mh_status", "mh_params", "mh_ctx"})
+    assert len(declared) >= 35
+    lib = ctypes.CDLL(mh.library_path())
+    missing = [s for s in declared if not hasattr(lib, s)]
+    assert not missing, missing
+    assert sorted(declared) == sorted(mh.capi.SYMBOLS)
+
+
+def test_no_cpu_fallback(mh):
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present: the failure path is for CPU-only boxes")
+    with pytest.raises(mh.MHError) as e:
+        mh.Context()
+    assert e.value.status == mh.capi.MH_ECUDA
+
+
+def test_default_params_match_reference_cli(mh):
+    p = mh.capi.default_params()  # main.cpp:55-59, MultiH.h:13-15
+    assert (p.thr_fundamental, p.thr_homography, p.locality, p.lambda_, p.min_inliers) == (2.6, 2.2, 0.005, 0.5, 20)
+    assert (p.straightness, p.max_iterations, p.convergence, p.max_gc_cycles, p.max_neighbours) == (0.005, 500, 1e-5, 1000, 31)
+
+
+def test_neighbourhood_matches_oracle(mh, orc):
+    sc = mh.scenes.make_scene(1500, 4, seed=21)
+    for radius, k in ((0.0, 31), (12.5, 0), (60.0, 0), (60.0, 31), (200.0, 31), (200.0, 5), (1e4, 31)):
+        o1, a1 = orc.radius_neighbours(sc.pts, radius, k)
+        o2, a2 = mh.capi.neighbourhood(sc.pts, radius, k)
+        assert np.array_equal(o1, o2) and np.array_equal(a1, a2), (radius, k)
+    assert np.diff(o2).max() == 31  # FLANN checks=32 cap
+
+
+@pytest.mark.parametrize("radius", [0.0, 15.0, 40.0])
+def test_alpha_expansion_equals_reference_gco(mh, orc, radius):
+    """Same dense costs + same graph => our host alpha-expansion returns the reference GCO's labels bit for bit."""
+    if orc.ref_lib() is None:
+        pytest.skip("oracle/_ref not built")
+    sc = mh.scenes.make_scene(2500, 6, seed=5)
+    H = np.concatenate([sc.planes, orc.haf_hypotheses(sc.pts[:30], sc.aff[:30], sc.F)])
+    cost = orc.data_cost_dense(sc.pts, H)
+    off, adj = mh.capi.neighbourhood(sc.pts, radius, 0 if radius < 20 else 31)
+    e_ref, l_ref = orc.gco_ref_expansion(cost, 50, off, adj)
+    l, e = mh.capi.alpha_expansion(cost, 50, off, adj)
+    assert e == e_ref
+    assert np.array_equal(l, l_ref)
+    init = np.roll(l_ref, 13)  # warm start (MultiH.cpp:525-529)
+    e_ref2, l_ref2 = orc.gco_ref_expansion(cost, 50, off, adj, init_labels=init)
+    l2, e2 = mh.capi.alpha_expansion(cost, 50, off, adj, init=init)
+    assert e2 == e_ref2 and np.array_equal(l2, l_ref2)
+
+
+def test_alpha_expansion_edge_cases(mh):
+    cost = np.array([[5, 1, 9], [2, 2, 2], [9, 8, 7]], dtype=np.int32)
+    l, e = mh.capi.alpha_expansion(cost, 50, np.zeros(4, dtype=np.int64), np.zeros(0, dtype=np.int32))
+    assert l.tolist() == [1, 0, 2] and e == 1 + 2 + 7  # no edges: per-site argmin, first label wins ties
+    # a strong edge pulls both sites to the jointly cheapest label; int64 totals do not overflow
+    big = np.array([[0, 2_000_000_000], [2_000_000_000, 1]], dtype=np.int32)
+    l, e = mh.capi.alpha_expansion(big, 2_000_000_000, np.array([0, 1, 2]), np.array([1, 0], dtype=np.int32))
+    assert e == 2_000_000_000 and l.tolist() == [0, 0]  # pair weight 2 x 2e9 exceeds int32
+    with pytest.raises(mh.MHError):
+        mh.capi.alpha_expansion(cost, 1, np.zeros(4, dtype=np.int64), np.zeros(0, dtype=np.int32), init=[0, 7, 0])
+
+
+def test_text_format_roundtrip(mh, tmp_path):
+    sc = mh.scenes.make_scene(20, 2, seed=1)
+    p = tmp_path / "pts.txt"
+    mh.scenes.save_points(str(p), sc.pts, sc.aff, sc.gt)
+    pts, aff, lab = mh.scenes.load_points(str(p))
+    assert np.allclose(pts, sc.pts, rtol=1e-5) and np.allclose(aff, sc.aff, rtol=1e-5, atol=1e-6)
+    assert np.array_equal(lab, sc.gt)

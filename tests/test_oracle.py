@@ -1,0 +1,140 @@
+"""CPU tests of the oracle (the FP64 restatement of the reference hot path): known-answer tests, the reference's integer
+cost constants, and the golden vectors produced by tests/golden/make_golden.py (an independent transliteration on top of
+the real OpenCV routines)."""
+import os
+
+import numpy as np
+import pytest
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.fixture(scope="module")
+def scene(mh):
+    return mh.scenes.make_scene(4000, 5, outlier_ratio=0.0, noise_px=0.0, noise_aff=0.0, seed=11)
+
+
+def test_scene_is_epipolar_consistent(scene):
+    x1 = np.c_[scene.pts[:, :2], np.ones(len(scene.pts))]
+    x2 = np.c_[scene.pts[:, 2:], np.ones(len(scene.pts))]
+    assert np.abs(np.einsum("ij,jk,ik->i", x2, scene.F, x1)).max() < 1e-9  # x2^T F x1 = 0
+
+
+def test_sym_eigen_matches_numpy(orc):
+    rng = np.random.default_rng(0)
+    for n in (3, 4):
+        A = rng.normal(size=(n, n)); A = A @ A.T
+        w, V = orc.sym_eigen(A)
+        wn = np.linalg.eigvalsh(A)[::-1]
+        assert np.allclose(w, wn, rtol=1e-12, atol=1e-12)            # descending, like cv::eigen
+        assert np.allclose(V @ A @ V.T, np.diag(w), atol=1e-10)       # eigenvectors in rows
+
+
+def test_haf_known_answer(orc, scene):
+    # noise-free plane: GetHomographyHAF (MultiH.cpp:850-911) must return the generating homography
+    H = orc.haf_hypotheses(scene.pts, scene.aff, scene.F)
+    ref = scene.planes[scene.gt]
+    assert (np.abs(H - ref).max(1) / np.abs(ref).max(1)).max() < 1e-6
+
+
+def test_3pt_and_refit_known_answer(orc, scene):
+    for p in range(5):
+        idx = np.where(scene.gt == p)[0][:12]
+        H = orc.homography_3pt(scene.pts[idx, :2], scene.pts[idx, 2:], scene.F).ravel()
+        assert np.abs(H / H[8] - scene.planes[p]).max() < 1e-7
+    Hr, M10, cnt = orc.refit_haf(scene.pts, scene.aff, scene.gt, 5, scene.F)
+    assert np.abs(Hr / Hr[:, 8:9] - scene.planes).max() < 1e-6
+    assert cnt.sum() == len(scene.pts)
+
+
+def test_cost_constants(orc, scene):
+    # default parameters (lambda 0.5, thr 2.2): outlier label 4901, beyond truncation 9802, inliers 0..200 and
+    # DEcreasing with distance; Potts 50 (MultiH.cpp:473-511, MultiH.h:41-44)
+    c = orc.data_cost_dense(scene.pts[:50], scene.planes)
+    assert (c[:, 0] == 4901).all()
+    own = c[np.arange(50), scene.gt[:50] + 1]
+    assert (own == 200).all()
+    other = np.delete(c, 0, axis=1)
+    assert set(np.unique(other)) <= set(range(0, 201)) | {9802}
+    assert orc.smooth_cost(1, 2) == 50 and orc.smooth_cost(3, 3) == 0
+    p = np.array([[0.0, 0.0, 3.0, 0.0]])
+    I = np.eye(3).ravel()[None]
+    d2, T = 9.0, 2.2 ** 2 * 81 / 16
+    assert orc.data_cost_dense(p, I)[0, 1] == int(np.floor(200 * (1 - d2 / T) + 0.5))
+
+
+def test_features_layout(orc, scene):
+    H = scene.planes[:3]
+    f6 = orc.features6(H)
+    f10 = orc.features10(H, scene.pts[:3], 0.005)
+    for k in range(3):
+        h = H[k].reshape(3, 3)
+        im = [h @ np.array(v) for v in ([0, 0, 1.0], [1, 0, 1.0], [0, 1, 1.0])]
+        im = [v[:2] / v[2] for v in im]
+        assert np.allclose(f6[k], np.concatenate(im))                                   # x1 y1 x2 y2 x3 y3
+        assert np.allclose(f10[k, :6], [im[0][0], im[1][0], im[2][0], im[0][1], im[1][1], im[2][1]])  # x1 x2 x3 y1 y2 y3
+        assert np.allclose(f10[k, 6:], 0.005 * scene.pts[k])
+
+
+def test_meanshift_semantics(orc):
+    # two well separated blobs; L1 window vs bw^2 (MeanShiftClustering.h:76-85); merge at bw/2 by averaging
+    rng = np.random.default_rng(3)
+    a = rng.normal(0, 0.05, size=(40, 6)); b = rng.normal(0, 0.05, size=(30, 6)) + 10.0
+    X = np.concatenate([a, b])
+    centres, assign, state, (traj, iters) = orc.meanshift(X, 2.2)
+    assert centres.shape[0] == 2 and traj == 2
+    assert len(set(assign[:40])) == 1 and len(set(assign[40:])) == 1 and assign[0] != assign[-1]
+    assert np.allclose(sorted(centres[:, 0]), [a[:, 0].mean(), b[:, 0].mean()], atol=1e-6)
+    # MSVC rand() restatement: first values of the unseeded generator are 41, 18467, 6334
+    hold, vals = 1, []
+    for _ in range(3):
+        hold = (hold * 214013 + 2531011) & 0xFFFFFFFF
+        vals.append((hold >> 16) & 0x7FFF)
+    assert vals == [41, 18467, 6334]
+
+
+def test_inlier_stats_straightness(orc, scene):
+    # points of one plane restricted to a line in image 1 => lambda_min ~ 0 => rejected (MultiH.cpp:445-463)
+    pts = scene.pts[scene.gt == 0][:200].copy()
+    H = scene.planes[:1]
+    cnt, sc, lmin, keep = orc.inlier_stats(pts, H)
+    assert cnt[0] == 200 and keep[0]
+    t = np.linspace(0, 1, 50)
+    line = np.stack([100 + 300 * t, 50 + 200 * t], 1)
+    h = H[0].reshape(3, 3)
+    q = (h @ np.c_[line, np.ones(50)].T).T
+    lp = np.c_[line, q[:, :2] / q[:, 2:]]
+    cnt, sc, lmin, keep = orc.inlier_stats(lp, H)
+    assert cnt[0] == 50 and lmin[0] < 0.005 and not keep[0]
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(GOLD, "golden_small.npz")), reason="golden vectors not generated")
+def test_golden_vectors(orc):
+    """tests/golden/golden_small.npz was produced by make_golden.py with cv2.eigen / cv2.invert(DECOMP_SVD) — the
+    OpenCV routines the reference calls (MultiH.cpp:893, 973, 1015, 1038)."""
+    g = np.load(os.path.join(GOLD, "golden_small.npz"))
+    pts, aff, F = g["pts"], g["aff"], g["F"]
+    assert np.allclose(orc.epipole2(F), g["e2"], rtol=1e-9)
+    H = orc.haf_hypotheses(pts, aff, F)
+    rel = np.abs(H - g["haf_H"]).max(1) / np.abs(g["haf_H"]).max(1)
+    assert np.percentile(rel, 99) < 1e-7 and rel.max() < 1e-4, (np.percentile(rel, 99), rel.max())
+    assert np.allclose(orc.features10(g["haf_H"], pts, 0.005), g["feat10"], rtol=1e-12, atol=1e-12)
+    assert np.allclose(orc.features6(g["haf_H"][:16]), g["feat6"], rtol=1e-12, atol=1e-12)
+    assert np.array_equal(orc.data_cost_dense(pts, g["cost_H"]), g["cost"])
+    for k in range(len(g["pt3_idx_padded"])):
+        idx = g["pt3_idx_padded"][k]
+        idx = idx[idx >= 0]
+        H3 = orc.homography_3pt(pts[idx, :2], pts[idx, 2:], F).ravel()
+        ref = g["pt3_H"][k]
+        assert np.abs(H3 / H3[8] - ref / ref[8]).max() / np.abs(ref / ref[8]).max() < 1e-6
+    Hr, _, cnt = orc.refit_haf(pts, aff, g["labels"], int(g["labels"].max()) + 1, F)
+    ref = g["refit_H"]
+    ok = cnt > 0
+    rel = np.abs(Hr[ok] / Hr[ok][:, 8:9] - ref[ok] / ref[ok][:, 8:9]).max(1) / np.abs(ref[ok] / ref[ok][:, 8:9]).max(1)
+    assert rel.max() < 1e-6
+    Hm = np.stack([orc.mode_to_homography(m, F).ravel() for m in g["modes"]])
+    ref = g["modes_H"]
+    assert (np.abs(Hm / Hm[:, 8:9] - ref / ref[:, 8:9]).max(1) / np.abs(ref / ref[:, 8:9]).max(1)).max() < 1e-6
+    cnt, sc, lmin, keep = orc.inlier_stats(pts, g["cost_H"])
+    assert np.array_equal(cnt, g["inl_count"]) and np.array_equal(keep, g["inl_keep"])
+    assert np.allclose(lmin, g["inl_lmin"], rtol=1e-6, atol=1e-9)
