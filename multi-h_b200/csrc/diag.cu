@@ -68,6 +68,8 @@ extern "C" mh_status mh_diag_fp32_peak(mh_ctx* ctx, int32_t variant, int32_t ite
   return MH_OK;
 }
 
-namespace mh { extern int g_fused_variant; }
+namespace mh { extern int g_fused_variant; extern int g_fast_config; }
 // 1 = packed FFMA2 inner loop (default), 0 = scalar FFMA (kept for A/B evidence)
 extern "C" mh_status mh_diag_set_fused_variant(mh_ctx*, int32_t v) { mh::g_fused_variant = v ? 1 : 0; return MH_OK; }
+// occupancy target of the K2 fast path: 0 = 3 CTAs/SM, 1 = 2, 2 = 4 (default)
+extern "C" mh_status mh_diag_set_fast_config(mh_ctx*, int32_t v) { mh::g_fast_config = v; return MH_OK; }

@@ -94,10 +94,10 @@ __global__ void __launch_bounds__(DENSE_THREADS) cost_dense_kernel(const float4*
     long long p = p0 + i;
     sp[i] = pts[p < N ? p : N - 1];
   }
-  float h[9];
+  float h[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   const bool valid = l < K;
-  {
-    const float4* hp = reinterpret_cast<const float4*>(hyp + (size_t)(valid ? l : 0) * 12);
+  if (valid) {
+    const float4* hp = reinterpret_cast<const float4*>(hyp + (size_t)l * 12);
     const float4 a = hp[0], b = hp[1], c = hp[2];
     h[0] = a.x; h[1] = a.y; h[2] = a.z; h[3] = a.w; h[4] = b.x; h[5] = b.y; h[6] = b.z; h[7] = b.w; h[8] = c.x;
   }
@@ -276,6 +276,181 @@ cost_fused_kernel(const float4* __restrict__ pts, long long N, const float* __re
   }
 }
 
+// ----------------------------------------------------------------------------
+// Fast path (no per-site lists): per-site data-term argmin + per-hypothesis inlier
+// counts, built for HIGH hit rates (on the 200-plane scene ~7 % of all residuals
+// are below the truncation threshold, so "emit on hit" is not a rare path).
+//
+//  * argmin: each thread keeps, per correspondence, the best (cost, label) so far
+//    and the d2 interval [lo, T) a residual must fall into to IMPROVE on it (lower
+//    integer cost; costs fall as d2 rises, MultiH.cpp:502).  The interval test is
+//    folded into the last FMA (t = d2 - mid, |t| < half), so the common path pays one
+//    FMNMX + one FSETP per hypothesis pair; the exact update (residual recomputed
+//    with the dense kernel's instruction sequence => bit-identical costs and ties)
+//    runs only on record-breaking candidates, ~ln(#hits) times per correspondence.
+//  * inlier counts: one FSETP + one predicated shared-memory RED per residual into a
+//    per-chunk counter array, flushed with one global RED per hypothesis and chunk.
+// Issue budget per residual: 5 FFMA2 + 1 MUFU + ~0.3 LDS + 1 (argmin filter) + 2
+// (inlier) ~ 9.5 slots against ~11 FMA-pipe cycles for the 5 FFMA2.
+// ----------------------------------------------------------------------------
+struct FastOut {
+  u64* best;             // [N] packed (cost << 32 | label), pre-initialised to (cost_outlier << 32 | 0)
+  int32_t* inlier_count; // [K]
+};
+
+__device__ __forceinline__ void fast_thresholds(int best_cost, const CostParams& cp, float& negmid, float& half) {
+  // a residual improves on best_cost iff cost(d2) <= best_cost - 1  <=>  d2 > T * (lam + 0.5 - best_cost) / lam
+  float lo = cp.T * (cp.lam + 0.5f - (float)best_cost) * (1.0f / cp.lam);
+  lo = fmaxf(lo, 0.f) * 0.9999f - 1e-12f;      // conservative: false positives are rejected by the exact update
+  const float hi = cp.T * 1.0001f;
+  negmid = -0.5f * (lo + hi);
+  half = 0.5f * (hi - lo);
+}
+
+// v3 register tile: 4 correspondences per thread x 2 hypothesis pairs (4 hypotheses) per iteration.
+constexpr int FAST_P = 4;
+constexpr int FAST_TILE = FUSED_THREADS * FAST_P;  // 1024 correspondences per CTA (=> per-CTA counts fit 16 bits)
+
+template <bool COUNT_INLIERS, int MINB>
+__global__ void __launch_bounds__(FUSED_THREADS, MINB)
+cost_argmin_kernel(const float4* __restrict__ pts, long long N, const float* __restrict__ hyp, int K, int k_per_block,
+                   CostParams cp, FastOut o, int use_atomic_best) {
+  __shared__ __align__(16) u64 sm[2][FUSED_CHUNK_PAIRS * 10];
+  __shared__ __align__(8) unsigned short s_cnt[2][2 * FUSED_CHUNK_PAIRS];  // per-chunk inlier counters (<= 1024 each)
+
+  const long long tile0 = (long long)blockIdx.x * FAST_TILE;
+  const int kbeg = blockIdx.y * k_per_block;
+  const int kend = min(K, kbeg + k_per_block);
+  const int lane = threadIdx.x & 31;
+
+  float X[FAST_P], Y[FAST_P], NX2[FAST_P], NY2[FAST_P], NEGMID[FAST_P], HALF[FAST_P], C[FAST_P];
+  int BC[FAST_P], BL[FAST_P];
+#pragma unroll
+  for (int p = 0; p < FAST_P; ++p) {
+    long long idx = tile0 + (long long)p * FUSED_THREADS + threadIdx.x;
+    const float4 q = pts[idx < N ? idx : N - 1];
+    X[p] = q.x; Y[p] = q.y; NX2[p] = -q.z; NY2[p] = -q.w;
+    BC[p] = cp.cost_outlier; BL[p] = 0;
+    fast_thresholds(BC[p], cp, NEGMID[p], HALF[p]);
+    C[p] = -NEGMID[p] - cp.thr2;  // (d2 - mid) + C = d2 - thr2: its sign bit is the inlier flag
+    if (idx >= N) { HALF[p] = -1.f; C[p] = 3.0e38f; BC[p] = -1; }  // padding lanes: never an inlier, never a candidate
+  }
+  const u64 ONE2 = pk(1.f, 1.f);
+
+  int buf = 0;
+  // chunks are padded to an even number of pairs with "far" hypotheses so that the loop can take two pairs at a time
+  auto pairs_in = [&](int c) { return min(FUSED_CHUNK_PAIRS, (((kend - c + 1) / 2) + 1) & ~1); };
+  stage_pairs(sm[0], hyp, kbeg, kend, pairs_in(kbeg));
+  if (COUNT_INLIERS)
+    for (int i = threadIdx.x; i < 4 * FUSED_CHUNK_PAIRS; i += FUSED_THREADS) (&s_cnt[0][0])[i] = 0;
+  __syncthreads();
+
+  for (int c0 = kbeg; c0 < kend; c0 += 2 * FUSED_CHUNK_PAIRS) {
+    const int npairs = pairs_in(c0);
+    const int cn = c0 + 2 * FUSED_CHUNK_PAIRS;
+    if (cn < kend) stage_pairs(sm[buf ^ 1], hyp, cn, kend, pairs_in(cn));
+
+    const ulonglong2* hp = reinterpret_cast<const ulonglong2*>(sm[buf]);
+    unsigned cnt_addr = (unsigned)__cvta_generic_to_shared(s_cnt[buf]);
+#pragma unroll 1
+    for (int j = 0; j < npairs; j += 2, hp += 10, cnt_addr += 8) {
+      u64 H[2][9];
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const ulonglong2 q0 = hp[5 * q], q1 = hp[5 * q + 1], q2 = hp[5 * q + 2], q3 = hp[5 * q + 3], q4 = hp[5 * q + 4];
+        H[q][0] = q0.x; H[q][1] = q0.y; H[q][2] = q1.x; H[q][3] = q1.y; H[q][4] = q2.x;
+        H[q][5] = q2.y; H[q][6] = q3.x; H[q][7] = q3.y; H[q][8] = q4.x;
+      }
+      bool any = false;
+      float M[2][FAST_P];
+      unsigned mask[4] = {0u, 0u, 0u, 0u};  // sign bits of (d2 - thr2): one bit per correspondence, per hypothesis
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+#pragma unroll
+        for (int p = 0; p < FAST_P; ++p) {
+          const u64 xx = pk(X[p], X[p]), yy = pk(Y[p], Y[p]);
+          const u64 sv = fma2(H[q][6], xx, fma2(H[q][7], yy, H[q][8]));
+          const u64 xn = fma2(H[q][0], xx, fma2(H[q][1], yy, H[q][2]));
+          const u64 yn = fma2(H[q][3], xx, fma2(H[q][4], yy, H[q][5]));
+          float sl, sh;
+          upk(sv, sl, sh);
+          const u64 r = pk(rcp_approx(sl), rcp_approx(sh));
+          const u64 dx = fma2(xn, r, pk(NX2[p], NX2[p]));
+          const u64 dy = fma2(yn, r, pk(NY2[p], NY2[p]));
+          const u64 t = fma2(dx, dx, fma2(dy, dy, pk(NEGMID[p], NEGMID[p])));  // d2 - mid
+          float ta, tb;
+          upk(t, ta, tb);
+          if (COUNT_INLIERS) {
+            float va, vb;
+            upk(fma2(t, ONE2, pk(C[p], C[p])), va, vb);  // d2 - thr2
+            mask[2 * q] = __funnelshift_l(__float_as_uint(va), mask[2 * q], 1);
+            mask[2 * q + 1] = __funnelshift_l(__float_as_uint(vb), mask[2 * q + 1], 1);
+          }
+          M[q][p] = fminf(fabsf(ta), fabsf(tb));
+          any = any || (M[q][p] < HALF[p]);
+        }
+      }
+      if (COUNT_INLIERS) {
+        // per-thread counts (<= 4) in byte fields -> one warp REDUX (<= 128 per field) -> one 64-bit shared RED of four
+        // 16-bit counters by lane 0
+        const unsigned bytes = __popc(mask[0]) | (__popc(mask[1]) << 8) | (__popc(mask[2]) << 16) | (__popc(mask[3]) << 24);
+        const unsigned tot = __reduce_add_sync(0xffffffffu, bytes);
+        const unsigned lo16 = __byte_perm(tot, 0u, 0x4140), hi16 = __byte_perm(tot, 0u, 0x4342);
+        asm volatile("{ .reg .pred p; .reg .b64 v;\n\t"
+                     "setp.eq.u32 p, %0, 0;\n\t"
+                     "mov.b64 v, {%2, %3};\n\t"
+                     "@p red.shared.add.u64 [%1], v; }"
+                     :: "r"(lane), "r"(cnt_addr), "r"(lo16), "r"(hi16) : "memory");
+      }
+      if (any) {  // a candidate may lower some correspondence's best cost: exact update (rare after warm-up)
+        float half_old[FAST_P];  // M[][] was measured against the thresholds in force before any update of this step
+#pragma unroll
+        for (int p = 0; p < FAST_P; ++p) half_old[p] = HALF[p];
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          float ha[9], hb[9];
+#pragma unroll
+          for (int k = 0; k < 9; ++k) upk(H[q][k], ha[k], hb[k]);
+          const int la = c0 + 2 * (j + q) + 1;  // 1-based label of lane a
+#pragma unroll
+          for (int p = 0; p < FAST_P; ++p) {
+            if (M[q][p] < half_old[p]) {
+              const float da = residual(ha, X[p], Y[p], -NX2[p], -NY2[p]);
+              const float db = residual(hb, X[p], Y[p], -NX2[p], -NY2[p]);
+              if (da < cp.T) { const int c = cost_in_range(da, cp); if (c < BC[p]) { BC[p] = c; BL[p] = la; } }
+              if (db < cp.T) { const int c = cost_in_range(db, cp); if (c < BC[p]) { BC[p] = c; BL[p] = la + 1; } }
+              fast_thresholds(BC[p], cp, NEGMID[p], HALF[p]);
+              C[p] = -NEGMID[p] - cp.thr2;
+            }
+          }
+        }
+      }
+    }
+    __syncthreads();
+    if (COUNT_INLIERS) {
+      unsigned short* cnt = s_cnt[buf];
+      for (int i = threadIdx.x; i < 2 * npairs; i += FUSED_THREADS) {
+        const int v = cnt[i];
+        cnt[i] = 0;
+        if (v && c0 + i < kend) atomicAdd(o.inlier_count + c0 + i, v);
+      }
+      // the zeroing above is ordered before the buffer's next use by the __syncthreads of the following iteration
+    }
+    buf ^= 1;
+  }
+  if (o.best) {
+#pragma unroll
+    for (int p = 0; p < FAST_P; ++p) {
+      const long long idx = tile0 + (long long)p * FUSED_THREADS + threadIdx.x;
+      if (idx < N && BL[p] != 0) {
+        const u64 v = ((u64)(uint32_t)BC[p] << 32) | (uint32_t)BL[p];
+        if (use_atomic_best) atomicMin(o.best + idx, v);
+        else o.best[idx] = v;
+      }
+    }
+  }
+}
+
 __global__ void fused_init_kernel(long long N, int K, int32_t* list_count, u64* best, int32_t* inlier_count,
                                   u64 best_init) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -287,6 +462,7 @@ __global__ void fused_init_kernel(long long N, int K, int32_t* list_count, u64* 
 }
 
 int g_fused_variant = 1;  // 1 = packed FFMA2 (default), 0 = scalar FFMA (A/B evidence)
+int g_fast_config = 2;    // occupancy target of the fast path: 0 = 3 CTAs/SM, 1 = 2, 2 = 4 (default; 64 regs)
 
 mh_status launch_cost_fused(mh_ctx* ctx, const float4* d_pts, int64_t N, const float* d_hyp, int K, int kmax,
                             uint32_t* d_list, int32_t* d_list_count, unsigned long long* d_best,
@@ -310,8 +486,29 @@ mh_status launch_cost_fused(mh_ctx* ctx, const float4* d_pts, int64_t N, const f
   int k_per_block = (K + ksplit - 1) / ksplit;
   k_per_block = (k_per_block + 1) & ~1;  // even, so label pairs stay aligned
   ksplit = (K + k_per_block - 1) / k_per_block;
-  FusedOut o{d_list, d_list_count, (u64*)d_best, d_inlier_count, kmax};
   dim3 grid(tiles, (unsigned)ksplit);
+  if (!d_list && !d_list_count && g_fused_variant == 1) {
+    FastOut fo{(u64*)d_best, d_inlier_count};
+    const unsigned tiles_f = (unsigned)((N + FAST_TILE - 1) / FAST_TILE);
+    int ks = 1;
+    if ((int)tiles_f < want) ks = std::min((K + 2 * FUSED_CHUNK_PAIRS - 1) / (2 * FUSED_CHUNK_PAIRS), (want + (int)tiles_f - 1) / (int)tiles_f);
+    ks = std::max(1, ks);
+    int kpb = (K + ks - 1) / ks;
+    kpb = (kpb + 3) & ~3;  // multiple of 4: pair-of-pairs alignment
+    ks = (K + kpb - 1) / kpb;
+    dim3 gridf(tiles_f, (unsigned)ks);
+#define MH_LAUNCH_FAST(CNT, MB) cost_argmin_kernel<CNT, MB><<<gridf, FUSED_THREADS, 0, ctx->stream>>>(d_pts, N, d_hyp, K, kpb, cp, fo, ks > 1)
+    const bool cnt = d_inlier_count != nullptr;
+    switch (g_fast_config) {
+      case 1: if (cnt) MH_LAUNCH_FAST(true, 2); else MH_LAUNCH_FAST(false, 2); break;
+      case 2: if (cnt) MH_LAUNCH_FAST(true, 4); else MH_LAUNCH_FAST(false, 4); break;
+      default: if (cnt) MH_LAUNCH_FAST(true, 3); else MH_LAUNCH_FAST(false, 3); break;
+    }
+#undef MH_LAUNCH_FAST
+    MH_LAUNCHED(ctx, "cost_argmin_kernel");
+    return MH_OK;
+  }
+  FusedOut o{d_list, d_list_count, (u64*)d_best, d_inlier_count, kmax};
   if (g_fused_variant)
     cost_fused_kernel<true><<<grid, FUSED_THREADS, 0, ctx->stream>>>(d_pts, N, d_hyp, K, k_per_block, cp, o);
   else

@@ -132,6 +132,29 @@ def test_k2_fused_equals_dense(gpu_ctx, dev, scene, hyps):
     gpu_ctx.set_fused_variant(1)
 
 
+def test_k2_fast_argmin_and_inlier_counts(gpu_ctx, dev, scene, hyps, mh):
+    """The list-free fast path (what bench.py times): argmin bit-exact vs the dense matrix, inlier counts vs FP32 residuals."""
+    import torch
+
+    gpu_ctx.set_geometry(scene.F, scene.pts)
+    d_hyp = gpu_ctx.hypotheses_from_host(hyps)
+    cg = gpu_ctx.data_cost_dense(dev[0], d_hyp).cpu().numpy()
+    rg = gpu_ctx.residuals(dev[0], d_hyp).cpu().numpy()
+    f = gpu_ctx.data_cost_fused(dev[0], d_hyp, kmax=0, want_list=False, out={})
+    best = f["best"].cpu().numpy()
+    assert np.array_equal(best & 0xFFFFFFFF, cg.argmin(1))
+    assert np.array_equal(best >> 32, cg.min(1))
+    inl = f["inliers"].cpu().numpy()
+    ref = (rg < np.float32(2.2 ** 2)).sum(0)
+    assert np.abs(inl - ref).max() <= 2 and abs(int(inl.sum()) - int(ref.sum())) <= 8
+    # many hypotheses, few correspondences: the K range is split over CTAs and merged with atomicMin
+    big = torch.cat([d_hyp] * 9)[:2049].contiguous()
+    cgb = gpu_ctx.data_cost_dense(dev[0][:3000].contiguous(), big).cpu().numpy()
+    fb = gpu_ctx.data_cost_fused(dev[0][:3000].contiguous(), big, kmax=0, want_list=False, out={})
+    assert np.array_equal(fb["best"].cpu().numpy() & 0xFFFFFFFF, cgb.argmin(1))
+    assert np.array_equal(fb["best"].cpu().numpy() >> 32, cgb.min(1))
+
+
 def test_k2_edge_cases(gpu_ctx, dev, scene, mh):
     import torch
 
