@@ -8,8 +8,8 @@ of randomly chosen correspondences), correspondence-sharded over the ranks (stro
 One "step" = one pass of the hot path over the scene:
     K1  HAF hypothesis per correspondence                    (MultiH.cpp:696-717, 850-911)
     [N>1] NCCL broadcast of the 8192 x 12 hypothesis block from rank 0
-    K2  fused N x K residual / data cost: per-site data-term argmin label + cost, per-site in-range count,
-        per-hypothesis inlier count — nothing N x K touches HBM (MultiH.cpp:473-504, 430-443, 743-768)
+    K2  fused N x K residual / data cost: per-site data-term argmin label + cost and per-hypothesis inlier
+        count — nothing N x K touches HBM (MultiH.cpp:473-504, 430-443, 743-768)
     [N>1] NCCL all-reduce of the K inlier counts
     K4  per-label refit statistics from the argmin labels (segmented reduction of SUM A^T A)
     [N>1] NCCL all-reduce of the K x 12 FP64 statistics
@@ -170,8 +170,7 @@ def main():
         d_hyp[N_PLANES:] = ctx.haf_hypotheses(p_pts, p_aff)
         del p_pts, p_aff
     d_hyp_pt = torch.empty((n_loc, 12), dtype=torch.float32, device=dev)
-    fused = {"count": torch.empty(n_loc, dtype=torch.int32, device=dev),
-             "best": torch.empty(n_loc, dtype=torch.int64, device=dev),
+    fused = {"best": torch.empty(n_loc, dtype=torch.int64, device=dev),
              "inliers": torch.empty(K_HYP, dtype=torch.int32, device=dev)}
     labels = torch.empty(n_loc, dtype=torch.int32, device=dev)
     acc = torch.empty((K_HYP, 12), dtype=torch.float64, device=dev)
@@ -276,7 +275,7 @@ def main():
         except Exception:
             traffic = None
     roofline = {"bound": "fp32", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                "traffic": traffic, "kernel": "cost_fused_kernel",
+                "traffic": traffic, "kernel": "cost_argmin_kernel",
                 "algorithmic": f"{FLOP_PER_RESIDUAL} flop/residual x {n_loc} x {K_HYP} per launch",
                 "kernel_ms": k2_ms, "kernel_share_of_step": k2_ms / ms_per_step,
                 "peak_source": "measured in this run: dependent-FFMA probe (mh_diag_fp32_peak), "

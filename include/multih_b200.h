@@ -63,6 +63,8 @@ typedef struct mh_params {
   int32_t max_gc_cycles;  /* expansion(iter, 1000)  (MultiH.cpp:543)                           */
   int32_t max_neighbours; /* 31: FLANN default checks=32 caps radiusMatch (MultiH.cpp:252-253) at the ~31 nearest
                              other sites inside the radius; <= 0 = the full radius ball                      */
+  int32_t precise_pipeline; /* mh_process data path: 1 (default) = FP64 pixel-space kernels tracking the reference's
+                               arithmetic; 0 = FP32 normalised throughput kernels (same control flow)        */
 } mh_params;
 
 void mh_default_params(mh_params* p); /* main.cpp:55-59: 2.6 / 2.2 / 0.005 / 0.5 / 20 */

@@ -43,7 +43,7 @@ class Params(C.Structure):
         ("thr_fundamental", C.c_double), ("thr_homography", C.c_double), ("locality", C.c_double),
         ("lambda_", C.c_double), ("min_inliers", C.c_int32), ("straightness", C.c_double),
         ("max_iterations", C.c_int32), ("convergence", C.c_double), ("meanshift_metric", C.c_int32),
-        ("rng_seed", C.c_uint32), ("max_gc_cycles", C.c_int32), ("max_neighbours", C.c_int32),
+        ("rng_seed", C.c_uint32), ("max_gc_cycles", C.c_int32), ("max_neighbours", C.c_int32), ("precise_pipeline", C.c_int32),
     ]
 
 
@@ -255,7 +255,7 @@ class Context:
         t = self.torch
         N, K = d_pts.shape[0], d_hyp.shape[0]
         o = out or {}
-        if "count" not in o and (want_list or out is None):
+        if "count" not in o and want_list:
             o["count"] = self._empty((N,), t.int32)
         if want_list and "list" not in o:
             o["list"] = self._empty((N, max(kmax, 1)), t.int32)
@@ -264,7 +264,8 @@ class Context:
         if want_inliers and "inliers" not in o:
             o["inliers"] = self._empty((K,), t.int32)
         self._check(lib().mh_data_cost_fused(self._h, _vp(d_pts), C.c_int64(N), _vp(d_hyp), K, int(kmax),
-                                             _vp(o.get("list") if want_list else None), _vp(o.get("count")),
+                                             _vp(o.get("list") if want_list else None),
+                                             _vp(o.get("count") if want_list else None),
                                              _vp(o.get("best") if want_best else None),
                                              _vp(o.get("inliers") if want_inliers else None)))
         return o

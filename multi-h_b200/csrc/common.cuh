@@ -97,7 +97,10 @@ void sym_eigen3_host(const double* A, double* w, double* Vrows);
 // ---- kernel launchers (defined in the k*.cu files) -------------------------
 mh_status launch_normalize_points(mh_ctx*, const double* d_pts_raw, const double* d_aff_raw, int64_t N, float4* d_pts,
                                   float4* d_aff);
-mh_status launch_haf(mh_ctx*, const float4* d_pts, const float4* d_aff, int64_t N, float* d_hyp, int precision);
+// Trailing FP64 pointers select the PRECISE path used by mh_process: raw FP64 pixel correspondences in, FP64 pixel-space
+// homographies out (next to the FP32 normalised ones), so that the alternating optimisation tracks the FP64 reference.
+mh_status launch_haf(mh_ctx*, const float4* d_pts, const float4* d_aff, int64_t N, float* d_hyp, int precision,
+                     const double* d_pts64 = nullptr, const double* d_aff64 = nullptr, double* d_hyp64 = nullptr);
 mh_status launch_cost_dense(mh_ctx*, const float4* d_pts, int64_t N, const float* d_hyp, int K, void* d_cost,
                             int elem_bytes);
 mh_status launch_residuals(mh_ctx*, const float4* d_pts, int64_t N, const float* d_hyp, int K, float* d_d2);
@@ -107,17 +110,27 @@ mh_status launch_cost_fused(mh_ctx*, const float4* d_pts, int64_t N, const float
 mh_status launch_inlier_stats(mh_ctx*, const float4* d_pts, int64_t N, const float* d_hyp, int K,
                               double* d_scatter /*K x 6, normalised coords*/);
 mh_status launch_inliers_of(mh_ctx*, const float4* d_pts, int64_t N, const float* d_hyp_one, int idx, int32_t* d_labels);
-mh_status launch_features10(mh_ctx*, const float* d_hyp, const float4* d_pts, int64_t N, double* d_feat);
-mh_status launch_features6(mh_ctx*, const float* d_hyp, int K, double* d_feat);
+mh_status launch_features10(mh_ctx*, const float* d_hyp, const float4* d_pts, int64_t N, double* d_feat,
+                            const double* d_hyp64 = nullptr, const double* d_pts64 = nullptr);
+mh_status launch_features6(mh_ctx*, const float* d_hyp, int K, double* d_feat, const double* d_hyp64 = nullptr);
 mh_status launch_meanshift(mh_ctx*, const double* d_feat, int N, int D, double bw, int metric, uint32_t* rng_state,
                            double* d_centres, int max_c, int32_t* d_assign, int* C_out, int64_t* stats);
 mh_status launch_refit_haf(mh_ctx*, const float4* d_pts, const float4* d_aff, const int32_t* d_labels, int64_t N, int K,
-                           float* d_hyp, int32_t* d_count);
+                           float* d_hyp, int32_t* d_count, const double* d_pts64 = nullptr,
+                           const double* d_aff64 = nullptr, double* d_hyp64 = nullptr);
 mh_status launch_refit_haf_accumulate(mh_ctx*, const float4* d_pts, const float4* d_aff, const int32_t* d_labels,
-                                      int64_t N, int K, double* d_acc);
-mh_status launch_refit_haf_solve(mh_ctx*, const double* d_acc, int K, float* d_hyp, int32_t* d_count);
+                                      int64_t N, int K, double* d_acc, const double* d_pts64 = nullptr,
+                                      const double* d_aff64 = nullptr);
+mh_status launch_refit_haf_solve(mh_ctx*, const double* d_acc, int K, float* d_hyp, int32_t* d_count,
+                                 double* d_hyp64 = nullptr);
 mh_status launch_refit_3pt(mh_ctx*, const float4* d_pts, const int32_t* d_assign, int64_t N, int C, float* d_hyp,
-                           int32_t* d_keep);
-mh_status launch_modes_to_hyp(mh_ctx*, const double* d_modes, int C, float* d_hyp);
+                           int32_t* d_keep, const double* d_pts64 = nullptr, double* d_hyp64 = nullptr);
+mh_status launch_modes_to_hyp(mh_ctx*, const double* d_modes, int C, float* d_hyp, double* d_hyp64 = nullptr);
+// FP64 members of the K2 family for the precise path (small N x K only): dataEnergy, inlier scan, single-H inliers
+mh_status launch_cost_dense64(mh_ctx*, const double* d_pts64, int64_t N, const double* d_hyp64, int K, int32_t* d_cost);
+mh_status launch_inlier_stats64(mh_ctx*, const double* d_pts64, int64_t N, const double* d_hyp64, int K,
+                                double* d_scatter /*K x 6, pixel coords*/);
+mh_status launch_inliers_of64(mh_ctx*, const double* d_pts64, int64_t N, const double* d_hyp64_one, int idx,
+                              int32_t* d_labels);
 
 }  // namespace mh

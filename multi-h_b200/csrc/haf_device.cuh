@@ -114,7 +114,8 @@ __device__ __forceinline__ void haf_accumulate(double x1, double y1, double x2, 
 }
 
 // H_px from v (MultiH.cpp:899-909), then H' = T2 H_px T1^-1 scaled by `scale`, stored as 12 floats
-__device__ __forceinline__ void haf_store(const double (&v)[4], const HafGeom& g, bool divide_h33, float* out) {
+__device__ __forceinline__ void haf_store(const double (&v)[4], const HafGeom& g, bool divide_h33, float* out,
+                                          double* out64 = nullptr) {
   double H[9];
   H[6] = v[0]; H[7] = v[1]; H[8] = v[2];
   const double lam = v[3];
@@ -128,6 +129,11 @@ __device__ __forceinline__ void haf_store(const double (&v)[4], const HafGeom& g
 #pragma unroll
     for (int k = 0; k < 9; ++k) m = fmax(m, fabs(H[k]));
     sc = m > 0.0 ? 1.0 / m : 1.0;
+  }
+  if (out64) {  // precise path: the pixel-space FP64 homography exactly as the reference holds it
+    const double s64 = divide_h33 ? sc : 1.0;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) out64[k] = H[k] * s64;
   }
   // G = H_px T1^-1 : T1^-1 = [1/s1 0 -t1x/s1; 0 1/s1 -t1y/s1; 0 0 1]
   const double is1 = 1.0 / g.s1;
@@ -172,6 +178,41 @@ __device__ __forceinline__ void hyp_to_pixel(const float* __restrict__ hp, const
     H[c2] = (G[c2] - g.t2x * G[6 + c2]) * is2;
     H[3 + c2] = (G[3 + c2] - g.t2y * G[6 + c2]) * is2;
     H[6 + c2] = G[6 + c2];
+  }
+}
+
+// ---- point / hypothesis sources: FP32 normalised device-space, or (precise path) raw FP64 pixels ------------------
+__device__ __forceinline__ void load_point_px(const float4* __restrict__ pts, const double* __restrict__ pts64, long long i,
+                                              const HafGeom& g, double& x1, double& y1, double& x2, double& y2) {
+  if (pts64) {
+    const double2* p = reinterpret_cast<const double2*>(pts64 + 4 * i);
+    const double2 a = p[0], b = p[1];
+    x1 = a.x; y1 = a.y; x2 = b.x; y2 = b.y;
+  } else {
+    const float4 p = pts[i];
+    x1 = ((double)p.x - g.t1x) / g.s1; y1 = ((double)p.y - g.t1y) / g.s1;
+    x2 = ((double)p.z - g.t2x) / g.s2; y2 = ((double)p.w - g.t2y) / g.s2;
+  }
+}
+__device__ __forceinline__ void load_affine_px(const float4* __restrict__ aff, const double* __restrict__ aff64, long long i,
+                                               const HafGeom& g, double& a11, double& a12, double& a21, double& a22) {
+  if (aff64) {
+    const double2* p = reinterpret_cast<const double2*>(aff64 + 4 * i);
+    const double2 a = p[0], b = p[1];
+    a11 = a.x; a12 = a.y; a21 = b.x; a22 = b.y;
+  } else {
+    const float4 a = aff[i];
+    const double ra = g.s1 / g.s2;
+    a11 = a.x * ra; a12 = a.y * ra; a21 = a.z * ra; a22 = a.w * ra;
+  }
+}
+__device__ __forceinline__ void load_hyp_px(const float* __restrict__ hyp, const double* __restrict__ hyp64, long long i,
+                                            const HafGeom& g, double (&H)[9]) {
+  if (hyp64) {
+#pragma unroll
+    for (int k = 0; k < 9; ++k) H[k] = hyp64[9 * i + k];
+  } else {
+    hyp_to_pixel(hyp + 12 * i, g, H);
   }
 }
 

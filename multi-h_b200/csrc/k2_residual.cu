@@ -588,4 +588,101 @@ mh_status launch_inliers_of(mh_ctx* ctx, const float4* d_pts, int64_t N, const f
   return MH_OK;
 }
 
+// ============================================================================
+// FP64 members of the family, for the PRECISE path of mh_process (N x K small): the alternating optimisation is
+// chaotic — one +-1 cost can flip a cut, move a refit and change the next merge — so the pipeline evaluates
+// dataEnergy / the inlier scans exactly as the reference does (FP64, pixel coordinates).  Not a throughput path.
+// ============================================================================
+__device__ __forceinline__ double residual64(const double* __restrict__ h, double x, double y, double x2, double y2) {
+  const double s1 = h[6] * x + h[7] * y + h[8];                      // MultiH.cpp:491-498, operation for operation
+  const double x1 = (h[0] * x + h[1] * y + h[2]) / s1;
+  const double y1 = (h[3] * x + h[4] * y + h[5]) / s1;
+  const double dx = x1 - x2, dy = y1 - y2;
+  return dx * dx + dy * dy;
+}
+
+__global__ void cost_dense64_kernel(const double* __restrict__ pts, long long N, const double* __restrict__ hyp, int K,
+                                    int32_t* __restrict__ out, double lam, double T, int cost_outlier, int cost_far) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long L = K + 1;
+  if (e >= N * L) return;
+  const long long p = e / L;
+  const int l = (int)(e % L);
+  if (l == 0) { out[e] = cost_outlier; return; }
+  const double* q = pts + 4 * p;
+  const double d = residual64(hyp + 9 * (size_t)(l - 1), q[0], q[1], q[2], q[3]);
+  out[e] = (d < T) ? (int)round(lam * (1.0 - d / T)) : cost_far;     // MultiH.cpp:501-503 (C round(): half away)
+}
+
+mh_status launch_cost_dense64(mh_ctx* ctx, const double* d_pts64, int64_t N, const double* d_hyp64, int K, int32_t* d_cost) {
+  if (N <= 0) return MH_OK;
+  const double thr2 = ctx->params.thr_homography * ctx->params.thr_homography, T = thr2 * 81.0 / 16.0;
+  const double lam = 100.0 / ctx->params.lambda;
+  const int c0 = (int)std::round(lam * T);
+  const long long total = (long long)N * (K + 1);
+  cost_dense64_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(d_pts64, N, d_hyp64, K, d_cost, lam, T, c0, 2 * c0);
+  MH_LAUNCHED(ctx, "cost_dense64_kernel");
+  return MH_OK;
+}
+
+__global__ void __launch_bounds__(STATS_THREADS) inlier_stats64_kernel(const double* __restrict__ pts, long long N,
+                                                                       const double* __restrict__ hyp, int K,
+                                                                       double* __restrict__ scatter, double thr2) {
+  const long long idx = (long long)blockIdx.x * STATS_THREADS + threadIdx.x;
+  const bool live = idx < N;
+  const double* q = pts + 4 * (live ? idx : N - 1);
+  const double x = q[0], y = q[1], x2 = q[2], y2 = q[3];
+  const int lane = threadIdx.x & 31;
+  for (int k = 0; k < K; ++k) {
+    const double h6 = hyp[9 * (size_t)k + 6], h7 = hyp[9 * (size_t)k + 7], h8 = hyp[9 * (size_t)k + 8];
+    const double s = h6 * x + h7 * y + h8;                          // MultiH.cpp:434-441
+    const double x1 = (hyp[9 * (size_t)k] * x + hyp[9 * (size_t)k + 1] * y + hyp[9 * (size_t)k + 2]) / s;
+    const double y1 = (hyp[9 * (size_t)k + 3] * x + hyp[9 * (size_t)k + 4] * y + hyp[9 * (size_t)k + 5]) / s;
+    const double dx = x2 - x1, dy = y2 - y1;
+    const bool in = live && (dx * dx + dy * dy < thr2);
+    const unsigned b = __ballot_sync(0xffffffffu, in);
+    if (b == 0) continue;
+    double v[5] = {in ? x * x : 0.0, in ? x * y : 0.0, in ? x : 0.0, in ? y * y : 0.0, in ? y : 0.0};
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1)
+#pragma unroll
+      for (int t = 0; t < 5; ++t) v[t] += __shfl_xor_sync(0xffffffffu, v[t], off);
+    if (lane == 0) {
+      double* o = scatter + 6 * (size_t)k;
+#pragma unroll
+      for (int t = 0; t < 5; ++t) atomicAdd(o + t, v[t]);
+      atomicAdd(o + 5, (double)__popc(b));
+    }
+  }
+}
+
+mh_status launch_inlier_stats64(mh_ctx* ctx, const double* d_pts64, int64_t N, const double* d_hyp64, int K,
+                                double* d_scatter) {
+  if (K <= 0) return MH_OK;
+  MH_CUDA(ctx, cudaMemsetAsync(d_scatter, 0, sizeof(double) * 6 * (size_t)K, ctx->stream));
+  if (N <= 0) return MH_OK;
+  const double thr2 = ctx->params.thr_homography * ctx->params.thr_homography;
+  inlier_stats64_kernel<<<(unsigned)((N + STATS_THREADS - 1) / STATS_THREADS), STATS_THREADS, 0, ctx->stream>>>(
+      d_pts64, N, d_hyp64, K, d_scatter, thr2);
+  MH_LAUNCHED(ctx, "inlier_stats64_kernel");
+  return MH_OK;
+}
+
+__global__ void inliers_of64_kernel(const double* __restrict__ pts, long long N, const double* __restrict__ h, int idx,
+                                    int32_t* __restrict__ labels, double thr2) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  const double* q = pts + 4 * i;
+  if (residual64(h, q[0], q[1], q[2], q[3]) < thr2) labels[i] = idx;   // MultiH.cpp:753-763
+}
+
+mh_status launch_inliers_of64(mh_ctx* ctx, const double* d_pts64, int64_t N, const double* d_hyp64_one, int idx,
+                              int32_t* d_labels) {
+  if (N <= 0) return MH_OK;
+  const double thr2 = ctx->params.thr_homography * ctx->params.thr_homography;
+  inliers_of64_kernel<<<(unsigned)((N + 255) / 256), 256, 0, ctx->stream>>>(d_pts64, N, d_hyp64_one, idx, d_labels, thr2);
+  MH_LAUNCHED(ctx, "inliers_of64_kernel");
+  return MH_OK;
+}
+
 }  // namespace mh

@@ -134,7 +134,9 @@ __global__ void __launch_bounds__(256) haf_segment_accumulate_kernel(const float
                                                                      const int32_t* __restrict__ members,
                                                                      const int32_t* __restrict__ sorted_label,
                                                                      const int32_t* __restrict__ offsets, int K,
-                                                                     double* __restrict__ acc, HafGeom g) {
+                                                                     double* __restrict__ acc, HafGeom g,
+                                                                     const double* __restrict__ pts64,
+                                                                     const double* __restrict__ aff64) {
   const int M = offsets[K];
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31;
@@ -145,15 +147,15 @@ __global__ void __launch_bounds__(256) haf_segment_accumulate_kernel(const float
   for (int k = 0; k < 10; ++k) v[k] = 0.0;
   if (live) {
     const int i = members[j];
-    const float4 p = pts[i], a = aff[i];
-    const double is1 = 1.0 / g.s1, is2 = 1.0 / g.s2, ra = g.s1 / g.s2;
+    double x1, y1, x2, y2, a11, a12, a21, a22;
+    load_point_px(pts, pts64, i, g, x1, y1, x2, y2);
+    load_affine_px(aff, aff64, i, g, a11, a12, a21, a22);
     double Mx[4][4];
 #pragma unroll
     for (int r = 0; r < 4; ++r)
 #pragma unroll
       for (int c = 0; c < 4; ++c) Mx[r][c] = 0.0;
-    haf_accumulate(((double)p.x - g.t1x) * is1, ((double)p.y - g.t1y) * is1, ((double)p.z - g.t2x) * is2,
-                   ((double)p.w - g.t2y) * is2, a.x * ra, a.y * ra, a.z * ra, a.w * ra, g, Mx);
+    haf_accumulate(x1, y1, x2, y2, a11, a12, a21, a22, g, Mx);
     int q = 0;
 #pragma unroll
     for (int r = 0; r < 4; ++r)
@@ -189,7 +191,7 @@ __global__ void acc_count_kernel(const int32_t* __restrict__ count, int K, doubl
 }
 
 __global__ void haf_solve_kernel(const double* __restrict__ acc, int K, float* __restrict__ hyp,
-                                 int32_t* __restrict__ count_out, HafGeom g) {
+                                 int32_t* __restrict__ count_out, HafGeom g, double* __restrict__ hyp64) {
   const int l = blockIdx.x * blockDim.x + threadIdx.x;
   if (l >= K) return;
   const double* a = acc + 12 * (size_t)l;
@@ -204,11 +206,11 @@ __global__ void haf_solve_kernel(const double* __restrict__ acc, int K, float* _
     for (int c = r; c < 4; ++c) { M[r][c] = a[q]; M[c][r] = a[q]; ++q; }
   double v[4];
   smallest_eigvec4(M, v);
-  haf_store(v, g, false, hyp + 12 * (size_t)l);  // no division by h33 (MultiH.cpp:977-989)
+  haf_store(v, g, false, hyp + 12 * (size_t)l, hyp64 ? hyp64 + 9 * (size_t)l : nullptr);  // no division by h33 (MultiH.cpp:977-989)
 }
 
 mh_status launch_refit_haf_accumulate(mh_ctx* ctx, const float4* d_pts, const float4* d_aff, const int32_t* d_labels,
-                                      int64_t N, int K, double* d_acc) {
+                                      int64_t N, int K, double* d_acc, const double* d_pts64, const double* d_aff64) {
   if (K <= 0) return MH_OK;
   if (N > 0x7fffffff) return fail(ctx, MH_EINVAL, "mh_refit_haf: N must fit int32");
   Csr c;
@@ -217,7 +219,8 @@ mh_status launch_refit_haf_accumulate(mh_ctx* ctx, const float4* d_pts, const fl
   const HafGeom g = haf_geom(ctx);
   if (N > 0) {
     haf_segment_accumulate_kernel<<<(unsigned)((N + 255) / 256), 256, 0, ctx->stream>>>(d_pts, d_aff, c.members,
-                                                                                        c.sorted_label, c.offsets, K, d_acc, g);
+                                                                                        c.sorted_label, c.offsets, K, d_acc, g,
+                                                                                        d_pts64, d_aff64);
     MH_LAUNCHED(ctx, "haf_segment_accumulate_kernel");
   }
   acc_count_kernel<<<(unsigned)((K + 255) / 256), 256, 0, ctx->stream>>>(c.count, K, d_acc);
@@ -225,20 +228,31 @@ mh_status launch_refit_haf_accumulate(mh_ctx* ctx, const float4* d_pts, const fl
   return MH_OK;
 }
 
-mh_status launch_refit_haf_solve(mh_ctx* ctx, const double* d_acc, int K, float* d_hyp, int32_t* d_count) {
+mh_status launch_refit_haf_solve(mh_ctx* ctx, const double* d_acc, int K, float* d_hyp, int32_t* d_count, double* d_hyp64) {
   if (K <= 0) return MH_OK;
-  haf_solve_kernel<<<(unsigned)((K + 63) / 64), 64, 0, ctx->stream>>>(d_acc, K, d_hyp, d_count, haf_geom(ctx));
+  haf_solve_kernel<<<(unsigned)((K + 63) / 64), 64, 0, ctx->stream>>>(d_acc, K, d_hyp, d_count, haf_geom(ctx), d_hyp64);
   MH_LAUNCHED(ctx, "haf_solve_kernel");
   return MH_OK;
 }
 
 mh_status launch_refit_haf(mh_ctx* ctx, const float4* d_pts, const float4* d_aff, const int32_t* d_labels, int64_t N,
-                           int K, float* d_hyp, int32_t* d_count) {
+                           int K, float* d_hyp, int32_t* d_count, const double* d_pts64, const double* d_aff64,
+                           double* d_hyp64) {
   if (K <= 0) return MH_OK;
-  MH_TRY(ensure_staging(ctx, sizeof(double) * 12 * (uint64_t)K));
-  double* acc = (double*)ctx->staging;
-  MH_TRY(launch_refit_haf_accumulate(ctx, d_pts, d_aff, d_labels, N, K, acc));
-  return launch_refit_haf_solve(ctx, acc, K, d_hyp, d_count);
+  // the statistics live behind the CSR arrays in the scratch arena (build_csr reserves K x 12 doubles at its head)
+  Csr c;
+  MH_TRY(build_csr(ctx, d_labels, N, K, c));
+  double* acc = c.acc;
+  const HafGeom g = haf_geom(ctx);
+  if (N > 0) {
+    haf_segment_accumulate_kernel<<<(unsigned)((N + 255) / 256), 256, 0, ctx->stream>>>(d_pts, d_aff, c.members,
+                                                                                        c.sorted_label, c.offsets, K, acc, g,
+                                                                                        d_pts64, d_aff64);
+    MH_LAUNCHED(ctx, "haf_segment_accumulate_kernel");
+  }
+  acc_count_kernel<<<(unsigned)((K + 255) / 256), 256, 0, ctx->stream>>>(c.count, K, acc);
+  MH_LAUNCHED(ctx, "acc_count_kernel");
+  return launch_refit_haf_solve(ctx, acc, K, d_hyp, d_count, d_hyp64);
 }
 
 // ---- 3PT -------------------------------------------------------------------------
@@ -308,7 +322,8 @@ __device__ __forceinline__ void pinv_normal3(const double (&Nq)[6], const double
 }
 
 __device__ __forceinline__ void assemble_3pt_and_store(const double (&h3)[3], const double (&Fn)[9], double ex, double ey,
-                                                       const Norm2& n, const HafGeom& g, float* out) {
+                                                       const Norm2& n, const HafGeom& g, float* out,
+                                                       double* out64 = nullptr) {
   // MultiH.cpp:1040-1050 (lambda == 1), then H = T2^-1 Hn T1 (MultiH.cpp:1054)
   double Hn[9];
   Hn[6] = h3[0]; Hn[7] = h3[1]; Hn[8] = h3[2];
@@ -319,6 +334,10 @@ __device__ __forceinline__ void assemble_3pt_and_store(const double (&h3)[3], co
   double H[9];
   mat3_mul_d(T2i, Hn, H);
   mat3_mul_d(H, T1, H);
+  if (out64) {
+#pragma unroll
+    for (int k = 0; k < 9; ++k) out64[k] = H[k];
+  }
   // pixel H -> context-normalised FP32 (free scale): H' = Tc2 H Tc1^-1
   const double C2[9] = {g.s2, 0, g.t2x, 0, g.s2, g.t2y, 0, 0, 1};
   const double C1i[9] = {1.0 / g.s1, 0, -g.t1x / g.s1, 0, 1.0 / g.s1, -g.t1y / g.s1, 0, 0, 1};
@@ -350,7 +369,8 @@ __device__ __forceinline__ void rows_3pt(double x1, double y1, double x2, double
 __global__ void __launch_bounds__(128) cluster_3pt_kernel(const float4* __restrict__ pts,
                                                           const int32_t* __restrict__ members,
                                                           const int32_t* __restrict__ offsets, int C,
-                                                          float* __restrict__ hyp, int32_t* __restrict__ keep, HafGeom g) {
+                                                          float* __restrict__ hyp, int32_t* __restrict__ keep, HafGeom g,
+                                                          const double* __restrict__ pts64, double* __restrict__ hyp64) {
   const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (c >= C) return;
@@ -359,22 +379,21 @@ __global__ void __launch_bounds__(128) cluster_3pt_kernel(const float4* __restri
     if (lane == 0) keep[c] = 0;
     return;
   }
-  const double is1 = 1.0 / g.s1, is2 = 1.0 / g.s2;
   // pass 1: centroids (3PTcb.h:166-168)
   double sx1 = 0, sy1 = 0, sx2 = 0, sy2 = 0;
   for (int j = beg + lane; j < end; j += 32) {
-    const float4 p = pts[members[j]];
-    sx1 += ((double)p.x - g.t1x) * is1; sy1 += ((double)p.y - g.t1y) * is1;
-    sx2 += ((double)p.z - g.t2x) * is2; sy2 += ((double)p.w - g.t2y) * is2;
+    double px1, py1, px2, py2;
+    load_point_px(pts, pts64, members[j], g, px1, py1, px2, py2);
+    sx1 += px1; sy1 += py1; sx2 += px2; sy2 += py2;
   }
   Norm2 nm;
   nm.mx1 = warp_sum(sx1) / n; nm.my1 = warp_sum(sy1) / n; nm.mx2 = warp_sum(sx2) / n; nm.my2 = warp_sum(sy2) / n;
   // pass 2: mean distance to the centroid (3PTcb.h:171-179)
   double d1 = 0, d2 = 0;
   for (int j = beg + lane; j < end; j += 32) {
-    const float4 p = pts[members[j]];
-    const double x1 = ((double)p.x - g.t1x) * is1 - nm.mx1, y1 = ((double)p.y - g.t1y) * is1 - nm.my1;
-    const double x2 = ((double)p.z - g.t2x) * is2 - nm.mx2, y2 = ((double)p.w - g.t2y) * is2 - nm.my2;
+    double px1, py1, px2, py2;
+    load_point_px(pts, pts64, members[j], g, px1, py1, px2, py2);
+    const double x1 = px1 - nm.mx1, y1 = py1 - nm.my1, x2 = px2 - nm.mx2, y2 = py2 - nm.my2;
     d1 += sqrt(x1 * x1 + y1 * y1);
     d2 += sqrt(x2 * x2 + y2 * y2);
   }
@@ -385,9 +404,10 @@ __global__ void __launch_bounds__(128) cluster_3pt_kernel(const float4* __restri
   // pass 3: normal equations
   double Nq[6] = {0, 0, 0, 0, 0, 0}, r[3] = {0, 0, 0};
   for (int j = beg + lane; j < end; j += 32) {
-    const float4 p = pts[members[j]];
-    const double x1 = (((double)p.x - g.t1x) * is1 - nm.mx1) * nm.s1, y1 = (((double)p.y - g.t1y) * is1 - nm.my1) * nm.s1;
-    const double x2 = (((double)p.z - g.t2x) * is2 - nm.mx2) * nm.s2, y2 = (((double)p.w - g.t2y) * is2 - nm.my2) * nm.s2;
+    double px1, py1, px2, py2;
+    load_point_px(pts, pts64, members[j], g, px1, py1, px2, py2);
+    const double x1 = (px1 - nm.mx1) * nm.s1, y1 = (py1 - nm.my1) * nm.s1;
+    const double x2 = (px2 - nm.mx2) * nm.s2, y2 = (py2 - nm.my2) * nm.s2;
     rows_3pt(x1, y1, x2, y2, ex, ey, Fn, Nq, r);
   }
 #pragma unroll
@@ -397,25 +417,27 @@ __global__ void __launch_bounds__(128) cluster_3pt_kernel(const float4* __restri
   if (lane == 0) {
     double h3[3];
     pinv_normal3(Nq, r, h3);
-    assemble_3pt_and_store(h3, Fn, ex, ey, nm, g, hyp + 12 * (size_t)c);
+    assemble_3pt_and_store(h3, Fn, ex, ey, nm, g, hyp + 12 * (size_t)c, hyp64 ? hyp64 + 9 * (size_t)c : nullptr);
     keep[c] = 1;
   }
 }
 
 mh_status launch_refit_3pt(mh_ctx* ctx, const float4* d_pts, const int32_t* d_assign, int64_t N, int C, float* d_hyp,
-                           int32_t* d_keep) {
+                           int32_t* d_keep, const double* d_pts64, double* d_hyp64) {
   if (C <= 0) return MH_OK;
   if (N > 0x7fffffff) return fail(ctx, MH_EINVAL, "mh_refit_3pt: N must fit int32");
   Csr c;
   MH_TRY(build_csr(ctx, d_assign, N, C, c));
   const unsigned blocks = (unsigned)(((uint64_t)C * 32 + 127) / 128);
-  cluster_3pt_kernel<<<blocks, 128, 0, ctx->stream>>>(d_pts, c.members, c.offsets, C, d_hyp, d_keep, haf_geom(ctx));
+  cluster_3pt_kernel<<<blocks, 128, 0, ctx->stream>>>(d_pts, c.members, c.offsets, C, d_hyp, d_keep, haf_geom(ctx), d_pts64,
+                                                      d_hyp64);
   MH_LAUNCHED(ctx, "cluster_3pt_kernel");
   return MH_OK;
 }
 
 // MergingStep: mode (6-D feature, pixel units) -> homography by 3PT on (0,0),(1,0),(0,1) (MultiH.cpp:408-427).
-__global__ void modes_to_hyp_kernel(const double* __restrict__ modes, int C, float* __restrict__ hyp, HafGeom g) {
+__global__ void modes_to_hyp_kernel(const double* __restrict__ modes, int C, float* __restrict__ hyp, HafGeom g,
+                                    double* __restrict__ hyp64) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   const double* m = modes + 6 * (size_t)c;
@@ -442,12 +464,12 @@ __global__ void modes_to_hyp_kernel(const double* __restrict__ modes, int C, flo
              (p2[i][1] - nm.my2) * nm.s2, ex, ey, Fn, Nq, r);
   double h3[3];
   pinv_normal3(Nq, r, h3);
-  assemble_3pt_and_store(h3, Fn, ex, ey, nm, g, hyp + 12 * (size_t)c);
+  assemble_3pt_and_store(h3, Fn, ex, ey, nm, g, hyp + 12 * (size_t)c, hyp64 ? hyp64 + 9 * (size_t)c : nullptr);
 }
 
-mh_status launch_modes_to_hyp(mh_ctx* ctx, const double* d_modes, int C, float* d_hyp) {
+mh_status launch_modes_to_hyp(mh_ctx* ctx, const double* d_modes, int C, float* d_hyp, double* d_hyp64) {
   if (C <= 0) return MH_OK;
-  modes_to_hyp_kernel<<<(unsigned)((C + 63) / 64), 64, 0, ctx->stream>>>(d_modes, C, d_hyp, haf_geom(ctx));
+  modes_to_hyp_kernel<<<(unsigned)((C + 63) / 64), 64, 0, ctx->stream>>>(d_modes, C, d_hyp, haf_geom(ctx), d_hyp64);
   MH_LAUNCHED(ctx, "modes_to_hyp_kernel");
   return MH_OK;
 }

@@ -13,6 +13,8 @@
 // ============================================================================
 #include <chrono>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -71,43 +73,68 @@ mh_status mh_process(mh_ctx* ctx, const double* pts, const double* aff, const do
   if (N < 8) return fail(ctx, MH_EINVAL, "Error: Features are not set! (MultiH.cpp:44-50: fewer than 8 correspondences)");
   *K_out = 0;
   const mh_params& P = ctx->params;
+  const bool trace = std::getenv("MH_TRACE") != nullptr;  // the reference's LOG_TO_CONSOLE (MultiH.h:18, MultiH.cpp:292-293)
+  // precise = 1 (default): FP64 pixel-space data path on the device, tracking the reference's arithmetic; 0: FP32
+  // normalised data path (the throughput kernels) — same control flow, results equal up to FP32 rounding.
+  const bool precise = P.precise_pipeline != 0;
   const double t_start = now_ms();
   MH_TRY(mh_set_geometry(ctx, F, nullptr, nullptr, pts, N));
 
-  DevBuf b_pts, b_aff, b_hyp_pt, b_feat, b_centres, b_assign, b_hyp, b_keep, b_cost, b_labels, b_modes_hyp, b_feat6;
+  DevBuf b_pts, b_aff, b_pts64, b_aff64, b_hyp_pt, b_hyp_pt64, b_feat, b_centres, b_assign, b_hyp, b_hyp64, b_keep, b_cost,
+      b_labels, b_modes_hyp, b_modes_hyp64, b_feat6, b_scatter;
   MH_TRY(b_pts.alloc(ctx, sizeof(float4) * (uint64_t)N));
   MH_TRY(b_aff.alloc(ctx, sizeof(float4) * (uint64_t)N));
-  MH_TRY(mh_upload_correspondences(ctx, pts, aff, N, b_pts.p, b_aff.p));
+  MH_TRY(b_pts64.alloc(ctx, sizeof(double) * 4 * (uint64_t)N));
+  MH_TRY(b_aff64.alloc(ctx, sizeof(double) * 4 * (uint64_t)N));
+  MH_CUDA(ctx, cudaMemcpyAsync(b_pts64.p, pts, sizeof(double) * 4 * (size_t)N, cudaMemcpyHostToDevice, ctx->stream));
+  MH_CUDA(ctx, cudaMemcpyAsync(b_aff64.p, aff, sizeof(double) * 4 * (size_t)N, cudaMemcpyHostToDevice, ctx->stream));
+  MH_TRY(launch_normalize_points(ctx, b_pts64.as<double>(), b_aff64.as<double>(), N, b_pts.as<float4>(), b_aff.as<float4>()));
+  const double* pts64 = precise ? b_pts64.as<double>() : nullptr;
+  const double* aff64 = precise ? b_aff64.as<double>() : nullptr;
 
   // ---- ComputeLocalHomographies (MultiH.cpp:65, 696-717) ------------------------------
   double t0 = now_ms();
   MH_TRY(b_hyp_pt.alloc(ctx, sizeof(float) * 12 * (uint64_t)N));
-  MH_TRY(mh_haf_hypotheses(ctx, b_pts.p, b_aff.p, N, b_hyp_pt.p, 0));
+  if (precise) MH_TRY(b_hyp_pt64.alloc(ctx, sizeof(double) * 9 * (uint64_t)N));
+  MH_TRY(launch_haf(ctx, b_pts.as<float4>(), b_aff.as<float4>(), N, b_hyp_pt.as<float>(), 0, pts64, aff64,
+                    precise ? b_hyp_pt64.as<double>() : nullptr));
   MH_TRY(mh_sync(ctx));
   ctx->stage_ms[0] = now_ms() - t0;
 
   // ---- EstablishStablePointSets (MultiH.cpp:71, 604-694) ------------------------------
   t0 = now_ms();
   MH_TRY(b_feat.alloc(ctx, sizeof(double) * 10 * (uint64_t)N));
-  MH_TRY(mh_features10(ctx, b_hyp_pt.p, b_pts.p, N, b_feat.p));
+  MH_TRY(launch_features10(ctx, b_hyp_pt.as<float>(), b_pts.as<float4>(), N, b_feat.as<double>(),
+                           precise ? b_hyp_pt64.as<double>() : nullptr, pts64));
   MH_TRY(b_centres.alloc(ctx, sizeof(double) * 10 * (uint64_t)N));
   MH_TRY(b_assign.alloc(ctx, sizeof(int32_t) * (uint64_t)N));
   int32_t C = 0;
   MH_TRY(mh_meanshift(ctx, b_feat.p, N, 10, P.thr_homography, b_centres.p, N, b_assign.p, &C, nullptr));
-  std::vector<float> hyp;  // current cluster homographies, K x 12 (normalised space)
+  // current cluster homographies: K x 12 FP32 normalised (hyp) and, on the precise path, K x 9 FP64 pixels (hyp64)
+  std::vector<float> hyp;
+  std::vector<double> hyp64;
   int K = 0;
   if (C > 0) {
     MH_TRY(b_hyp.alloc(ctx, sizeof(float) * 12 * (uint64_t)C));
+    MH_TRY(b_hyp64.alloc(ctx, sizeof(double) * 9 * (uint64_t)C));
     MH_TRY(b_keep.alloc(ctx, sizeof(int32_t) * (uint64_t)C));
-    MH_TRY(mh_refit_3pt(ctx, b_pts.p, b_assign.p, N, C, b_hyp.p, b_keep.p));
+    MH_TRY(launch_refit_3pt(ctx, b_pts.as<float4>(), b_assign.as<int32_t>(), N, C, b_hyp.as<float>(), b_keep.as<int32_t>(),
+                            pts64, precise ? b_hyp64.as<double>() : nullptr));
     std::vector<float> all(12 * (size_t)C);
+    std::vector<double> all64(precise ? 9 * (size_t)C : 0);
     std::vector<int32_t> keep(C);
     MH_TRY(mh_memcpy_d2h(ctx, all.data(), b_hyp.p, sizeof(float) * 12 * (size_t)C));
+    if (precise) MH_TRY(mh_memcpy_d2h(ctx, all64.data(), b_hyp64.p, sizeof(double) * 9 * (size_t)C));
     MH_TRY(mh_memcpy_d2h(ctx, keep.data(), b_keep.p, sizeof(int32_t) * (size_t)C));
     for (int c = 0; c < C; ++c)
-      if (keep[c]) { hyp.insert(hyp.end(), all.begin() + 12 * (size_t)c, all.begin() + 12 * (size_t)(c + 1)); ++K; }
+      if (keep[c]) {
+        hyp.insert(hyp.end(), all.begin() + 12 * (size_t)c, all.begin() + 12 * (size_t)(c + 1));
+        if (precise) hyp64.insert(hyp64.end(), all64.begin() + 9 * (size_t)c, all64.begin() + 9 * (size_t)(c + 1));
+        ++K;
+      }
   }
   ctx->stage_ms[1] = now_ms() - t0;
+  if (trace) std::fprintf(stderr, "[mh_process] N = %d: %d mean-shift centres, %d stable clusters\n", N, C, K);
 
   // ---- neighbourhood (MultiH.cpp:231-258) ----------------------------------------------
   t0 = now_ms();
@@ -117,6 +144,17 @@ mh_status mh_process(mh_ctx* ctx, const double* pts, const double* aff, const do
   std::vector<int32_t> adj((size_t)std::max<int64_t>(total, 1));
   MH_TRY(mh_neighbourhood(ctx, pts, N, 1.0 / P.locality, P.max_neighbours, offsets.data(), adj.data(), &total));
   ctx->stage_ms[2] = now_ms() - t0;
+
+  // uploads the current hypothesis set (both representations)
+  auto upload_hyps = [&](int k) -> mh_status {
+    MH_TRY(b_hyp.alloc(ctx, sizeof(float) * 12 * (uint64_t)std::max(k, 1)));
+    MH_TRY(mh_memcpy_h2d(ctx, b_hyp.p, hyp.data(), sizeof(float) * 12 * (size_t)k));
+    if (precise) {
+      MH_TRY(b_hyp64.alloc(ctx, sizeof(double) * 9 * (uint64_t)std::max(k, 1)));
+      MH_TRY(mh_memcpy_h2d(ctx, b_hyp64.p, hyp64.data(), sizeof(double) * 9 * (size_t)k));
+    }
+    return MH_OK;
+  };
 
   // ---- alternating optimisation (MultiH.cpp:260-311) ------------------------------------
   t0 = now_ms();
@@ -131,36 +169,58 @@ mh_status mh_process(mh_ctx* ctx, const double* pts, const double* aff, const do
     bool changed = false;
     // -- MergingStep (MultiH.cpp:352-471)
     if (K > 0) {
-      MH_TRY(b_hyp.alloc(ctx, sizeof(float) * 12 * (uint64_t)K));
-      MH_TRY(mh_memcpy_h2d(ctx, b_hyp.p, hyp.data(), sizeof(float) * 12 * (size_t)K));
+      MH_TRY(upload_hyps(K));
       MH_TRY(b_feat6.alloc(ctx, sizeof(double) * 6 * (uint64_t)K));
-      MH_TRY(mh_features6(ctx, b_hyp.p, K, b_feat6.p));
+      MH_TRY(launch_features6(ctx, b_hyp.as<float>(), K, b_feat6.as<double>(), precise ? b_hyp64.as<double>() : nullptr));
       MH_TRY(b_centres.alloc(ctx, sizeof(double) * 6 * (uint64_t)K));
       MH_TRY(b_assign.alloc(ctx, sizeof(int32_t) * (uint64_t)K));
       int32_t Cm = 0;
       MH_TRY(mh_meanshift(ctx, b_feat6.p, K, 6, P.thr_homography, b_centres.p, K, b_assign.p, &Cm, nullptr));
       std::vector<float> merged;
+      std::vector<double> merged64;
       int Kn = 0;
       if (Cm > 0) {
         MH_TRY(b_modes_hyp.alloc(ctx, sizeof(float) * 12 * (uint64_t)Cm));
-        MH_TRY(mh_modes_to_hypotheses(ctx, b_centres.p, Cm, b_modes_hyp.p));
+        MH_TRY(b_modes_hyp64.alloc(ctx, sizeof(double) * 9 * (uint64_t)Cm));
+        MH_TRY(launch_modes_to_hyp(ctx, b_centres.as<double>(), Cm, b_modes_hyp.as<float>(),
+                                   precise ? b_modes_hyp64.as<double>() : nullptr));
         std::vector<int32_t> keep(Cm);
-        MH_TRY(mh_inlier_stats(ctx, b_pts.p, N, b_modes_hyp.p, Cm, nullptr, nullptr, keep.data()));
+        if (precise) {  // inlier scan + straightness test (MultiH.cpp:430-463) in FP64 pixel coordinates
+          MH_TRY(b_scatter.alloc(ctx, sizeof(double) * 6 * (uint64_t)Cm));
+          MH_TRY(launch_inlier_stats64(ctx, pts64, N, b_modes_hyp64.as<double>(), Cm, b_scatter.as<double>()));
+          std::vector<double> sc(6 * (size_t)Cm);
+          MH_TRY(mh_memcpy_d2h(ctx, sc.data(), b_scatter.p, sizeof(double) * 6 * (size_t)Cm));
+          for (int c = 0; c < Cm; ++c) {
+            const double* q = sc.data() + 6 * (size_t)c;
+            const double S[9] = {q[0], q[1], q[2], q[1], q[3], q[4], q[2], q[4], q[5]};
+            double w[3], V[9];
+            sym_eigen3_host(S, w, V);
+            keep[c] = !(w[2] < P.straightness || q[5] < 3.0);
+          }
+        } else {
+          MH_TRY(mh_inlier_stats(ctx, b_pts.p, N, b_modes_hyp.p, Cm, nullptr, nullptr, keep.data()));
+        }
         std::vector<float> all(12 * (size_t)Cm);
+        std::vector<double> all64(precise ? 9 * (size_t)Cm : 0);
         MH_TRY(mh_memcpy_d2h(ctx, all.data(), b_modes_hyp.p, sizeof(float) * 12 * (size_t)Cm));
+        if (precise) MH_TRY(mh_memcpy_d2h(ctx, all64.data(), b_modes_hyp64.p, sizeof(double) * 9 * (size_t)Cm));
         for (int c = 0; c < Cm; ++c)
-          if (keep[c]) { merged.insert(merged.end(), all.begin() + 12 * (size_t)c, all.begin() + 12 * (size_t)(c + 1)); ++Kn; }
+          if (keep[c]) {
+            merged.insert(merged.end(), all.begin() + 12 * (size_t)c, all.begin() + 12 * (size_t)(c + 1));
+            if (precise) merged64.insert(merged64.end(), all64.begin() + 9 * (size_t)c, all64.begin() + 9 * (size_t)(c + 1));
+            ++Kn;
+          }
       }
       changed = Kn != K;  // MultiH.cpp:468
-      if (changed) { hyp.swap(merged); K = Kn; }
+      if (changed) { hyp.swap(merged); hyp64.swap(merged64); K = Kn; }
     }
     if (changed) not_changed_number = 0; else ++not_changed_number;
 
     if (K == 1) {  // MultiH.cpp:280-285
-      MH_TRY(b_hyp.alloc(ctx, sizeof(float) * 12));
-      MH_TRY(mh_memcpy_h2d(ctx, b_hyp.p, hyp.data(), sizeof(float) * 12));
+      MH_TRY(upload_hyps(1));
       MH_TRY(mh_memcpy_h2d(ctx, b_labels.p, labeling.data(), sizeof(int32_t) * (size_t)N));
-      MH_TRY(mh_inliers_of_homography(ctx, b_pts.p, N, b_hyp.p, 0, b_labels.p));
+      if (precise) MH_TRY(launch_inliers_of64(ctx, pts64, N, b_hyp64.as<double>(), 0, b_labels.as<int32_t>()));
+      else MH_TRY(mh_inliers_of_homography(ctx, b_pts.p, N, b_hyp.p, 0, b_labels.p));
       MH_TRY(mh_memcpy_d2h(ctx, labeling.data(), b_labels.p, sizeof(int32_t) * (size_t)N));
       break;
     } else if (K == 0)
@@ -168,10 +228,10 @@ mh_status mh_process(mh_ctx* ctx, const double* pts, const double* aff, const do
 
     // -- LabelingStep (MultiH.cpp:513-602)
     const int L = K + 1;
-    MH_TRY(b_hyp.alloc(ctx, sizeof(float) * 12 * (uint64_t)K));
-    MH_TRY(mh_memcpy_h2d(ctx, b_hyp.p, hyp.data(), sizeof(float) * 12 * (size_t)K));
+    MH_TRY(upload_hyps(K));
     MH_TRY(b_cost.alloc(ctx, sizeof(int32_t) * (uint64_t)N * L));
-    MH_TRY(mh_data_cost_dense(ctx, b_pts.p, N, b_hyp.p, K, b_cost.p, 4));
+    if (precise) MH_TRY(launch_cost_dense64(ctx, pts64, N, b_hyp64.as<double>(), K, b_cost.as<int32_t>()));
+    else MH_TRY(mh_data_cost_dense(ctx, b_pts.p, N, b_hyp.p, K, b_cost.p, 4));
     cost.resize((size_t)N * L);
     MH_TRY(mh_memcpy_d2h(ctx, cost.data(), b_cost.p, sizeof(int32_t) * (size_t)N * L));
     const int32_t* init_ptr = nullptr;
@@ -183,10 +243,13 @@ mh_status mh_process(mh_ctx* ctx, const double* pts, const double* aff, const do
     MH_TRY(mh_alpha_expansion(ctx, cost.data(), N, L, potts, offsets.data(), adj.data(), init_ptr, P.max_gc_cycles,
                               gc_labels.data(), &e64));
     const double energy = (double)e64;
+    if (trace) std::fprintf(stderr, "[mh_process] iteration %d: K = %d changed = %d energy = %.0f\n", iteration_number, K, (int)changed, energy);
     for (int i = 0; i < N; ++i) labeling[i] = gc_labels[i] - 1;  // MultiH.cpp:547-568
     MH_TRY(mh_memcpy_h2d(ctx, b_labels.p, labeling.data(), sizeof(int32_t) * (size_t)N));
-    MH_TRY(mh_refit_haf(ctx, b_pts.p, b_aff.p, b_labels.p, N, K, b_hyp.p, nullptr));  // MultiH.cpp:587-599
+    MH_TRY(launch_refit_haf(ctx, b_pts.as<float4>(), b_aff.as<float4>(), b_labels.as<int32_t>(), N, K, b_hyp.as<float>(),
+                            nullptr, pts64, aff64, precise ? b_hyp64.as<double>() : nullptr));  // MultiH.cpp:587-599
     MH_TRY(mh_memcpy_d2h(ctx, hyp.data(), b_hyp.p, sizeof(float) * 12 * (size_t)K));
+    if (precise) MH_TRY(mh_memcpy_d2h(ctx, hyp64.data(), b_hyp64.p, sizeof(double) * 9 * (size_t)K));
 
     if ((!changed && std::fabs(lastEnergy - energy) < P.convergence) || not_changed_number > 10) {  // MultiH.cpp:295
       ctx->energy = energy;
@@ -199,9 +262,11 @@ mh_status mh_process(mh_ctx* ctx, const double* pts, const double* aff, const do
 
   std::memcpy(labels_out, labeling.data(), sizeof(int32_t) * (size_t)N);
   *K_out = K;
-  if (H_out) {
-    for (int k = 0; k < std::min(K, (int)Kmax); ++k) mh::hyp_norm_to_px(ctx, hyp.data() + 12 * (size_t)k, H_out + 9 * (size_t)k, false);
-  }
+  if (H_out)
+    for (int k = 0; k < std::min(K, (int)Kmax); ++k) {
+      if (precise) std::memcpy(H_out + 9 * (size_t)k, hyp64.data() + 9 * (size_t)k, sizeof(double) * 9);
+      else mh::hyp_norm_to_px(ctx, hyp.data() + 12 * (size_t)k, H_out + 9 * (size_t)k, false);
+    }
   ctx->stage_ms[4] = now_ms() - t_start;
   return MH_OK;
 }

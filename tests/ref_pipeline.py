@@ -64,4 +64,4 @@ def oracle_process(pts, aff, F, thr=2.2, locality=0.005, lam=0.5, straightness=0
             energy_final = energy
             break
         last_energy = energy
-    return labeling, hyp, dict(iterations=it - 0, energy=energy_final)
+    return labeling, hyp, dict(iterations=it - 1, energy=energy_final)  # final_iteration_number, MultiH.cpp:311
