@@ -195,7 +195,8 @@ mh_status mh_get_stage_ms(const mh_ctx* ctx, double ms[5]);
 mh_status mh_diag_fp32_peak(mh_ctx* ctx, int32_t variant, int32_t iters, double* tflops_out, double* ms_out);
 /* K2 fused inner loop: 1 = packed FFMA2 (default), 0 = scalar FFMA (A/B evidence only). */
 mh_status mh_diag_set_fused_variant(mh_ctx* ctx, int32_t variant);
-/* K2 fast path occupancy target: 0 = 3 CTAs/SM, 1 = 2, 2 = 4 (default) — tuning aid. */
+/* K2 fast path launch shape (threads/CTA x CTAs/SM): 0 = 256x3, 1 = 256x2, 2 = 256x4, 3 = 128x5, 4 = 128x6,
+ * 5 = 128x7 (default), 6 = 128x4 — tuning aid. */
 mh_status mh_diag_set_fast_config(mh_ctx* ctx, int32_t config);
 
 #ifdef __cplusplus

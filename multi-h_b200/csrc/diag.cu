@@ -71,5 +71,5 @@ extern "C" mh_status mh_diag_fp32_peak(mh_ctx* ctx, int32_t variant, int32_t ite
 namespace mh { extern int g_fused_variant; extern int g_fast_config; }
 // 1 = packed FFMA2 inner loop (default), 0 = scalar FFMA (kept for A/B evidence)
 extern "C" mh_status mh_diag_set_fused_variant(mh_ctx*, int32_t v) { mh::g_fused_variant = v ? 1 : 0; return MH_OK; }
-// occupancy target of the K2 fast path: 0 = 3 CTAs/SM, 1 = 2, 2 = 4 (default)
+// launch shape of the K2 fast path (threads/CTA x CTAs/SM): 0 = 256x3, 1 = 256x2, 2 = 256x4, 3 = 128x5, 4 = 128x6, 5 = 128x7 (default), 6 = 128x4
 extern "C" mh_status mh_diag_set_fast_config(mh_ctx*, int32_t v) { mh::g_fast_config = v; return MH_OK; }

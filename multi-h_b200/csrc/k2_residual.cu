@@ -308,17 +308,43 @@ __device__ __forceinline__ void fast_thresholds(int best_cost, const CostParams&
 }
 
 // v3 register tile: 4 correspondences per thread x 2 hypothesis pairs (4 hypotheses) per iteration.
-constexpr int FAST_P = 4;
-constexpr int FAST_TILE = FUSED_THREADS * FAST_P;  // 1024 correspondences per CTA (=> per-CTA counts fit 16 bits)
+constexpr int FAST_P = 4;  // <= 1024 correspondences per CTA => per-CTA inlier counts fit 16 bits
 
-template <bool COUNT_INLIERS, int MINB>
-__global__ void __launch_bounds__(FUSED_THREADS, MINB)
+// stage_pairs for an arbitrary CTA size
+template <int THREADS>
+__device__ __forceinline__ void stage_pairs_t(u64* sm, const float* __restrict__ hyp, int h0, int hend, int npairs) {
+  for (int j = threadIdx.x; j < npairs; j += THREADS) {
+    float a[9], b[9];
+    const int ia = h0 + 2 * j, ib = ia + 1;
+    if (ia < hend) {
+      const float4* p = reinterpret_cast<const float4*>(hyp + (size_t)ia * 12);
+      const float4 u = p[0], v = p[1], w = p[2];
+      a[0] = u.x; a[1] = u.y; a[2] = u.z; a[3] = u.w; a[4] = v.x; a[5] = v.y; a[6] = v.z; a[7] = v.w; a[8] = w.x;
+    } else {
+      a[0] = a[1] = a[3] = a[4] = a[6] = a[7] = 0.f; a[2] = a[5] = 1e18f; a[8] = 1.f;
+    }
+    if (ib < hend) {
+      const float4* p = reinterpret_cast<const float4*>(hyp + (size_t)ib * 12);
+      const float4 u = p[0], v = p[1], w = p[2];
+      b[0] = u.x; b[1] = u.y; b[2] = u.z; b[3] = u.w; b[4] = v.x; b[5] = v.y; b[6] = v.z; b[7] = v.w; b[8] = w.x;
+    } else {
+      b[0] = b[1] = b[3] = b[4] = b[6] = b[7] = 0.f; b[2] = b[5] = 1e18f; b[8] = 1.f;
+    }
+    u64* d = sm + (size_t)j * 10;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) d[k] = pk(a[k], b[k]);
+    d[9] = 0ull;
+  }
+}
+
+template <bool COUNT_INLIERS, int THREADS, int MINB, int CHUNK_PAIRS>
+__global__ void __launch_bounds__(THREADS, MINB)
 cost_argmin_kernel(const float4* __restrict__ pts, long long N, const float* __restrict__ hyp, int K, int k_per_block,
                    CostParams cp, FastOut o, int use_atomic_best) {
-  __shared__ __align__(16) u64 sm[2][FUSED_CHUNK_PAIRS * 10];
-  __shared__ __align__(8) unsigned short s_cnt[2][2 * FUSED_CHUNK_PAIRS];  // per-chunk inlier counters (<= 1024 each)
+  __shared__ __align__(16) u64 sm[2][CHUNK_PAIRS * 10];
+  __shared__ __align__(8) unsigned short s_cnt[2][2 * CHUNK_PAIRS];  // per-chunk inlier counters (<= 1024 each)
 
-  const long long tile0 = (long long)blockIdx.x * FAST_TILE;
+  const long long tile0 = (long long)blockIdx.x * (THREADS * FAST_P);
   const int kbeg = blockIdx.y * k_per_block;
   const int kend = min(K, kbeg + k_per_block);
   const int lane = threadIdx.x & 31;
@@ -327,7 +353,7 @@ cost_argmin_kernel(const float4* __restrict__ pts, long long N, const float* __r
   int BC[FAST_P], BL[FAST_P];
 #pragma unroll
   for (int p = 0; p < FAST_P; ++p) {
-    long long idx = tile0 + (long long)p * FUSED_THREADS + threadIdx.x;
+    long long idx = tile0 + (long long)p * THREADS + threadIdx.x;
     const float4 q = pts[idx < N ? idx : N - 1];
     X[p] = q.x; Y[p] = q.y; NX2[p] = -q.z; NY2[p] = -q.w;
     BC[p] = cp.cost_outlier; BL[p] = 0;
@@ -339,16 +365,16 @@ cost_argmin_kernel(const float4* __restrict__ pts, long long N, const float* __r
 
   int buf = 0;
   // chunks are padded to an even number of pairs with "far" hypotheses so that the loop can take two pairs at a time
-  auto pairs_in = [&](int c) { return min(FUSED_CHUNK_PAIRS, (((kend - c + 1) / 2) + 1) & ~1); };
-  stage_pairs(sm[0], hyp, kbeg, kend, pairs_in(kbeg));
+  auto pairs_in = [&](int c) { return min(CHUNK_PAIRS, (((kend - c + 1) / 2) + 1) & ~1); };
+  stage_pairs_t<THREADS>(sm[0], hyp, kbeg, kend, pairs_in(kbeg));
   if (COUNT_INLIERS)
-    for (int i = threadIdx.x; i < 4 * FUSED_CHUNK_PAIRS; i += FUSED_THREADS) (&s_cnt[0][0])[i] = 0;
+    for (int i = threadIdx.x; i < 4 * CHUNK_PAIRS; i += THREADS) (&s_cnt[0][0])[i] = 0;
   __syncthreads();
 
-  for (int c0 = kbeg; c0 < kend; c0 += 2 * FUSED_CHUNK_PAIRS) {
+  for (int c0 = kbeg; c0 < kend; c0 += 2 * CHUNK_PAIRS) {
     const int npairs = pairs_in(c0);
-    const int cn = c0 + 2 * FUSED_CHUNK_PAIRS;
-    if (cn < kend) stage_pairs(sm[buf ^ 1], hyp, cn, kend, pairs_in(cn));
+    const int cn = c0 + 2 * CHUNK_PAIRS;
+    if (cn < kend) stage_pairs_t<THREADS>(sm[buf ^ 1], hyp, cn, kend, pairs_in(cn));
 
     const ulonglong2* hp = reinterpret_cast<const ulonglong2*>(sm[buf]);
     unsigned cnt_addr = (unsigned)__cvta_generic_to_shared(s_cnt[buf]);
@@ -429,7 +455,7 @@ cost_argmin_kernel(const float4* __restrict__ pts, long long N, const float* __r
     __syncthreads();
     if (COUNT_INLIERS) {
       unsigned short* cnt = s_cnt[buf];
-      for (int i = threadIdx.x; i < 2 * npairs; i += FUSED_THREADS) {
+      for (int i = threadIdx.x; i < 2 * npairs; i += THREADS) {
         const int v = cnt[i];
         cnt[i] = 0;
         if (v && c0 + i < kend) atomicAdd(o.inlier_count + c0 + i, v);
@@ -441,7 +467,7 @@ cost_argmin_kernel(const float4* __restrict__ pts, long long N, const float* __r
   if (o.best) {
 #pragma unroll
     for (int p = 0; p < FAST_P; ++p) {
-      const long long idx = tile0 + (long long)p * FUSED_THREADS + threadIdx.x;
+      const long long idx = tile0 + (long long)p * THREADS + threadIdx.x;
       if (idx < N && BL[p] != 0) {
         const u64 v = ((u64)(uint32_t)BC[p] << 32) | (uint32_t)BL[p];
         if (use_atomic_best) atomicMin(o.best + idx, v);
@@ -462,7 +488,7 @@ __global__ void fused_init_kernel(long long N, int K, int32_t* list_count, u64* 
 }
 
 int g_fused_variant = 1;  // 1 = packed FFMA2 (default), 0 = scalar FFMA (A/B evidence)
-int g_fast_config = 2;    // occupancy target of the fast path: 0 = 3 CTAs/SM, 1 = 2, 2 = 4 (default; 64 regs)
+int g_fast_config = 5;    // (threads/CTA, CTAs/SM, chunk pairs) of the fast path, see launch_cost_fused; 5 = 128 x 7 x 128 (default)
 
 mh_status launch_cost_fused(mh_ctx* ctx, const float4* d_pts, int64_t N, const float* d_hyp, int K, int kmax,
                             uint32_t* d_list, int32_t* d_list_count, unsigned long long* d_best,
@@ -489,22 +515,31 @@ mh_status launch_cost_fused(mh_ctx* ctx, const float4* d_pts, int64_t N, const f
   dim3 grid(tiles, (unsigned)ksplit);
   if (!d_list && !d_list_count && g_fused_variant == 1) {
     FastOut fo{(u64*)d_best, d_inlier_count};
-    const unsigned tiles_f = (unsigned)((N + FAST_TILE - 1) / FAST_TILE);
-    int ks = 1;
-    if ((int)tiles_f < want) ks = std::min((K + 2 * FUSED_CHUNK_PAIRS - 1) / (2 * FUSED_CHUNK_PAIRS), (want + (int)tiles_f - 1) / (int)tiles_f);
-    ks = std::max(1, ks);
-    int kpb = (K + ks - 1) / ks;
-    kpb = (kpb + 3) & ~3;  // multiple of 4: pair-of-pairs alignment
-    ks = (K + kpb - 1) / kpb;
-    dim3 gridf(tiles_f, (unsigned)ks);
-#define MH_LAUNCH_FAST(CNT, MB) cost_argmin_kernel<CNT, MB><<<gridf, FUSED_THREADS, 0, ctx->stream>>>(d_pts, N, d_hyp, K, kpb, cp, fo, ks > 1)
     const bool cnt = d_inlier_count != nullptr;
+    // g_fast_config selects (threads per CTA, CTAs per SM, hypothesis pairs per staged chunk)
+    auto launch = [&](auto kernel_cnt, auto kernel_nocnt, int threads, int chunk_pairs) -> mh_status {
+      const long long tile = (long long)threads * FAST_P;
+      const unsigned tiles_f = (unsigned)((N + tile - 1) / tile);
+      int ks = 1;
+      if ((int)tiles_f < want) ks = std::min((K + 2 * chunk_pairs - 1) / (2 * chunk_pairs), (want + (int)tiles_f - 1) / (int)tiles_f);
+      ks = std::max(1, ks);
+      int kpb = (K + ks - 1) / ks;
+      kpb = (kpb + 3) & ~3;  // multiple of 4: pair-of-pairs alignment
+      ks = (K + kpb - 1) / kpb;
+      dim3 gridf(tiles_f, (unsigned)ks);
+      if (cnt) kernel_cnt<<<gridf, threads, 0, ctx->stream>>>(d_pts, N, d_hyp, K, kpb, cp, fo, ks > 1);
+      else kernel_nocnt<<<gridf, threads, 0, ctx->stream>>>(d_pts, N, d_hyp, K, kpb, cp, fo, ks > 1);
+      return MH_OK;
+    };
     switch (g_fast_config) {
-      case 1: if (cnt) MH_LAUNCH_FAST(true, 2); else MH_LAUNCH_FAST(false, 2); break;
-      case 2: if (cnt) MH_LAUNCH_FAST(true, 4); else MH_LAUNCH_FAST(false, 4); break;
-      default: if (cnt) MH_LAUNCH_FAST(true, 3); else MH_LAUNCH_FAST(false, 3); break;
+      case 0: launch(cost_argmin_kernel<true, 256, 3, 256>, cost_argmin_kernel<false, 256, 3, 256>, 256, 256); break;
+      case 1: launch(cost_argmin_kernel<true, 256, 2, 256>, cost_argmin_kernel<false, 256, 2, 256>, 256, 256); break;
+      case 3: launch(cost_argmin_kernel<true, 128, 5, 256>, cost_argmin_kernel<false, 128, 5, 256>, 128, 256); break;
+      case 4: launch(cost_argmin_kernel<true, 128, 6, 128>, cost_argmin_kernel<false, 128, 6, 128>, 128, 128); break;
+      case 5: launch(cost_argmin_kernel<true, 128, 7, 128>, cost_argmin_kernel<false, 128, 7, 128>, 128, 128); break;
+      case 6: launch(cost_argmin_kernel<true, 128, 4, 256>, cost_argmin_kernel<false, 128, 4, 256>, 128, 256); break;
+      default: launch(cost_argmin_kernel<true, 256, 4, 256>, cost_argmin_kernel<false, 256, 4, 256>, 256, 256); break;
     }
-#undef MH_LAUNCH_FAST
     MH_LAUNCHED(ctx, "cost_argmin_kernel");
     return MH_OK;
   }
