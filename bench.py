@@ -82,7 +82,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(name)
             except Exception:
                 pass
-            time.sleep(0.05)
+            time.sleep(0.004)
 
     def summary(self):
         return {"sm_mhz": (float(np.median(self.sm)) if self.sm else None), "sm_max_mhz": self.max_mhz,
@@ -271,7 +271,7 @@ def main():
     tpath = os.path.join(ROOT, "profiles", "k2_fused_traffic.json")
     if os.path.exists(tpath):
         try:
-            traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+            traffic = json.load(open(tpath)).get("dram_bytes_per_launch") * (n_loc / N_TOTAL)  # captured at 4M x 8192
         except Exception:
             traffic = None
     roofline = {"bound": "fp32", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
@@ -307,7 +307,7 @@ def main():
 
     # ---- CPU baseline (oracle port) on a bounded sample -----------------------------------------------------------------------
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:  # rank 0 at N=1 only
         from oracle import oracle as orc
 
         cores = orc.hardware_threads()

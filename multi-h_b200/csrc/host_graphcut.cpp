@@ -190,23 +190,37 @@ mh_status alpha_expansion(const int32_t* cost, int N, int L, int potts, const in
     return MH_OK;
   }
 
-  std::vector<int> var(N, -1), active;
+  // W[i] = largest amount the pairwise terms of site i can drop when i switches: a site whose data cost would rise by
+  // MORE than W[i] keeps its label in every minimiser of the move's binary energy, so it is fixed (x = 1) and left out of
+  // the flow network — an exact reduction that shrinks most moves to the few sites near hypothesis alpha.
+  std::vector<int64_t> W(N, 0);
+  for (int i = 0; i < N; ++i)
+    for (int64_t k = g.off[i]; k < g.off[i + 1]; ++k) W[i] += (int64_t)potts * g.w[k];
+
+  std::vector<int> var(N, -1), cand;
   std::vector<int32_t> trial(N);
+  std::vector<int64_t> src, snk;
   MaxFlow mf;
   int64_t E = total_energy(cost, N, L, potts, g, lab);
   if (max_cycles < 0) max_cycles = 1 << 30;
   for (int cycle = 0; cycle < max_cycles; ++cycle) {
     const int64_t E_old = E;
     for (int alpha = 0; alpha < L; ++alpha) {
-      active.clear();
+      cand.clear();
       for (int i = 0; i < N; ++i)
-        if (lab[i] != alpha) { var[i] = (int)active.size(); active.push_back(i); }
-      if (active.empty()) continue;
-      mf.reset((int)active.size(), (size_t)(g.off[N] + 2 * (int64_t)active.size()));
+        if (lab[i] != alpha && (int64_t)cost[(size_t)i * L + alpha] - cost[(size_t)i * L + lab[i]] <= W[i]) {
+          var[i] = (int)cand.size();
+          cand.push_back(i);
+        }
+      if (cand.empty()) continue;
+      size_t arcs = 0;
+      for (int i : cand) arcs += (size_t)(g.off[i + 1] - g.off[i]);
+      mf.reset((int)cand.size(), 2 * arcs + 2 * cand.size());
+      src.assign(cand.size(), 0);
+      snk.assign(cand.size(), 0);
       int64_t before = 0;
-      std::vector<int64_t> src(active.size(), 0), snk(active.size(), 0);
-      for (size_t a = 0; a < active.size(); ++a) {
-        const int i = active[a];
+      for (size_t a = 0; a < cand.size(); ++a) {
+        const int i = cand[a];
         // x = 0 (source side) takes alpha and pays E0 on the arc to the sink; x = 1 keeps its label
         snk[a] += cost[(size_t)i * L + alpha];
         src[a] += cost[(size_t)i * L + lab[i]];
@@ -214,41 +228,46 @@ mh_status alpha_expansion(const int32_t* cost, int N, int L, int potts, const in
         for (int64_t k = g.off[i]; k < g.off[i + 1]; ++k) {
           const int j = g.nbr[k];
           const int64_t w = (int64_t)potts * g.w[k];
-          if (var[j] < 0) {             // neighbour already alpha: pay w iff i keeps its label
+          if (lab[j] == alpha) {        // neighbour already alpha: pay w iff i keeps its label
             src[a] += w; before += w;
-          } else if (j < i) {           // both active: E00 = 0, E01 = w, E10 = w, E11 = w*[l_i != l_j]
-            const int b = var[j];
+          } else if (var[j] < 0) {      // neighbour keeps l_j != alpha for sure: alpha pays w, keeping pays w*[l_i != l_j]
+            const int64_t e1 = lab[i] != lab[j] ? w : 0;
+            snk[a] += w; src[a] += e1; before += e1;
+          } else if (j < i) {           // both in the network: E00 = 0, E01 = w, E10 = w, E11 = w*[l_i != l_j]
+            const int b2 = var[j];
             const int64_t e11 = lab[i] != lab[j] ? w : 0;
             before += e11;
-            // E(x_i, x_j) = e11*x_i*x_j-part ... decomposition: pay e11 on i's source arc, then arcs B = w, C = w - e11
-            src[a] += e11;
-            // remaining table: [0, w; w - e11, 0] -> arc i->j (x_i=0,x_j=1) = w, arc j->i (x_j=0, x_i=1) = w - e11
-            mf.add_edge((int)a, b, w, w - e11);
+            src[a] += e11;               // pay e11 on i's source arc, remaining table [0, w; w - e11, 0]
+            mf.add_edge((int)a, b2, w, w - e11);
           }
         }
       }
-      for (size_t a = 0; a < active.size(); ++a) mf.add_terminal((int)a, src[a], snk[a]);
+      for (size_t a = 0; a < cand.size(); ++a) mf.add_terminal((int)a, src[a], snk[a]);
       mf.solve();
-      for (int i = 0; i < N; ++i) trial[i] = lab[i];
-      for (size_t a = 0; a < active.size(); ++a)
-        if (!mf.sink_side((int)a)) trial[active[a]] = alpha;
-      // energy of the same terms under the trial labelling
-      int64_t after = 0;
-      for (size_t a = 0; a < active.size(); ++a) {
-        const int i = active[a];
-        after += cost[(size_t)i * L + trial[i]];
-        for (int64_t k = g.off[i]; k < g.off[i + 1]; ++k) {
-          const int j = g.nbr[k];
-          if (var[j] < 0 || j < i) {
-            if (trial[i] != trial[j]) after += (int64_t)potts * g.w[k];
+      bool any = false;
+      for (size_t a = 0; a < cand.size(); ++a) {
+        const bool sw = !mf.sink_side((int)a);
+        trial[cand[a]] = sw ? alpha : lab[cand[a]];
+        any |= sw;
+      }
+      if (any) {
+        // energy of the same terms under the trial labelling
+        int64_t after = 0;
+        for (size_t a = 0; a < cand.size(); ++a) {
+          const int i = cand[a];
+          after += cost[(size_t)i * L + trial[i]];
+          for (int64_t k = g.off[i]; k < g.off[i + 1]; ++k) {
+            const int j = g.nbr[k];
+            const int lj = var[j] >= 0 ? trial[j] : lab[j];
+            if ((var[j] < 0 || j < i) && trial[i] != lj) after += (int64_t)potts * g.w[k];
           }
         }
+        if (after < before) {
+          for (int i : cand) lab[i] = trial[i];
+          E += after - before;
+        }
       }
-      if (after < before) {
-        for (size_t a = 0; a < active.size(); ++a) lab[active[a]] = trial[active[a]];
-        E += after - before;
-      }
-      for (int i : active) var[i] = -1;
+      for (int i : cand) var[i] = -1;
     }
     if (E == E_old) break;
   }
