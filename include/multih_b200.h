@@ -94,7 +94,8 @@ mh_status mh_set_geometry(mh_ctx* ctx, const double F[9], const double norm1[3],
 mh_status mh_get_geometry(const mh_ctx* ctx, double F[9], double e2[2], double norm1[3], double norm2[3]);
 
 /* ---- host <-> device-space conversion ----------------------------------- */
-/* correspondences in the reference's layout (MultiH.h:78-80) -> normalised float4 arrays */
+/* correspondences in the reference's layout (MultiH.h:78-80) -> normalised float4 arrays.  Either half (points or
+ * affines: both of its pointers NULL) may be omitted so that the two uploads can be overlapped with compute. */
 mh_status mh_upload_correspondences(mh_ctx* ctx, const double* pts_host, const double* aff_host, int64_t N,
                                     void* d_pts, void* d_aff /* may be NULL */);
 mh_status mh_hypotheses_from_host(mh_ctx* ctx, const double* H_host /*K x 9 px*/, int32_t K, void* d_hyp);
@@ -142,6 +143,10 @@ mh_status mh_features6(mh_ctx* ctx, const void* d_hyp, int32_t K, void* d_feat /
 /* MeanShiftClustering<double>::Cluster (MeanShiftClustering.h:22-157): sequential-seed flat-kernel mean-shift, run as ONE
  * persistent cooperative kernel in FP64 (seeds drawn by the restated MSVC rand()).  d_centres f64 [max_c][D],
  * d_assign i32 [N] (cluster with most votes, first wins ties).  *C_out = number of centres. */
+/* The seed generator's state persists across mh_meanshift calls of a context (as rand() does in the reference process);
+ * mh_process re-seeds it from params.rng_seed on entry. */
+mh_status mh_set_rng_state(mh_ctx* ctx, uint32_t state);
+uint32_t mh_get_rng_state(const mh_ctx* ctx);
 mh_status mh_meanshift(mh_ctx* ctx, const void* d_feat, int32_t N, int32_t D, double bandwidth, void* d_centres,
                        int32_t max_c, void* d_assign, int32_t* C_out, int64_t* stats_out /*[2] or NULL*/);
 

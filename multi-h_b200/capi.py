@@ -25,7 +25,7 @@ SYMBOLS = [
     "mh_alloc", "mh_free", "mh_host_alloc", "mh_host_free", "mh_memcpy_d2h", "mh_memcpy_h2d", "mh_kernel_launches",
     "mh_set_geometry", "mh_get_geometry", "mh_upload_correspondences", "mh_hypotheses_from_host",
     "mh_hypotheses_to_host", "mh_haf_hypotheses", "mh_data_cost_dense", "mh_residuals", "mh_data_cost_fused",
-    "mh_inlier_stats", "mh_inliers_of_homography", "mh_features10", "mh_features6", "mh_meanshift", "mh_refit_haf",
+    "mh_inlier_stats", "mh_inliers_of_homography", "mh_features10", "mh_features6", "mh_set_rng_state", "mh_get_rng_state", "mh_meanshift", "mh_refit_haf",
     "mh_refit_haf_accumulate", "mh_refit_haf_solve", "mh_refit_3pt", "mh_modes_to_hypotheses", "mh_neighbourhood", "mh_alpha_expansion", "mh_process", "mh_get_energy",
     "mh_get_iterations", "mh_get_stage_ms", "mh_diag_fp32_peak", "mh_diag_set_fused_variant", "mh_diag_set_fast_config",
 ]
@@ -72,9 +72,11 @@ def lib():
         L.mh_kernel_launches.restype = C.c_int64
         L.mh_get_energy.restype = C.c_double
         L.mh_get_iterations.restype = C.c_int32
+        L.mh_get_rng_state.restype = C.c_uint32
         for name in SYMBOLS:
             fn = getattr(L, name)
             if name not in ("mh_last_error", "mh_version", "mh_kernel_launches", "mh_get_energy", "mh_get_iterations",
+                            "mh_get_rng_state",
                             "mh_default_params", "mh_destroy"):
                 fn.restype = C.c_int
         _lib = L
@@ -200,20 +202,29 @@ class Context:
         return F.reshape(3, 3), e2, n1, n2
 
     def upload(self, pts, aff=None, out=None):
-        """host FP64 correspondences (numpy or pinned torch CPU tensors) -> normalised float4 device arrays"""
+        """host FP64 correspondences (numpy or pinned torch CPU tensors) -> normalised float4 device arrays; `pts` or
+        `aff` may be None (upload only the other half)"""
         t = self.torch
-        N = pts.shape[0]
-        pp = C.c_void_p(pts.data_ptr()) if isinstance(pts, t.Tensor) else _p(_np(pts, np.float64), C.c_double)
-        pa = None
-        if aff is not None:
-            pa = C.c_void_p(aff.data_ptr()) if isinstance(aff, t.Tensor) else _p(_np(aff, np.float64), C.c_double)
+
+        def hp(a):
+            if a is None:
+                return None
+            return C.c_void_p(a.data_ptr()) if isinstance(a, t.Tensor) else _p(_np(a, np.float64), C.c_double)
+
+        N = (pts if pts is not None else aff).shape[0]
         if out is None:
-            d_pts = self._empty((N, 4), t.float32)
+            d_pts = self._empty((N, 4), t.float32) if pts is not None else None
             d_aff = self._empty((N, 4), t.float32) if aff is not None else None
         else:
             d_pts, d_aff = out
-        self._check(lib().mh_upload_correspondences(self._h, pp, pa, C.c_int64(N), _vp(d_pts), _vp(d_aff)))
+        self._check(lib().mh_upload_correspondences(self._h, hp(pts), hp(aff), C.c_int64(N),
+                                                    _vp(d_pts if pts is not None else None),
+                                                    _vp(d_aff if aff is not None else None)))
         return d_pts, d_aff
+
+    def use_stream(self, torch_stream):
+        """bind the context to a torch stream (mh_set_stream)"""
+        self._check(lib().mh_set_stream(self._h, C.c_void_p(torch_stream.cuda_stream)))
 
     def hypotheses_from_host(self, H):
         H = _np(H, np.float64).reshape(-1, 9)
@@ -283,6 +294,14 @@ class Context:
         return d_labels
 
     # -- K3
+    @property
+    def rng_state(self) -> int:
+        return int(lib().mh_get_rng_state(self._h))
+
+    @rng_state.setter
+    def rng_state(self, v: int):
+        self._check(lib().mh_set_rng_state(self._h, C.c_uint32(v)))
+
     def features10(self, d_hyp, d_pts):
         N = d_hyp.shape[0]
         d = self._empty((N, 10), self.torch.float64)

@@ -163,6 +163,7 @@ mh_status mh_create(const mh_params* params, int device, mh_ctx** out) {
   mh_ctx* ctx = new mh_ctx();
   if (params) ctx->params = *params; else mh_default_params(&ctx->params);
   ctx->device = device;
+  ctx->rng_state = ctx->params.rng_seed;
   if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return MH_ECUDA; }
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete ctx; return MH_ECUDA; }
@@ -310,15 +311,17 @@ mh_status mh_get_geometry(const mh_ctx* ctx, double F[9], double e2[2], double n
 mh_status mh_upload_correspondences(mh_ctx* ctx, const double* pts, const double* aff, int64_t N, void* d_pts,
                                     void* d_aff) {
   NEED_GEOM(ctx);
-  if (N < 0 || (N && (!pts || !d_pts)) || (d_aff && !aff)) return fail(ctx, MH_EINVAL, "mh_upload_correspondences: bad arguments");
+  // either half may be omitted (both pointers of a half NULL), so that a caller can overlap the two uploads with compute
+  if (N < 0 || (!pts != !d_pts) || (!aff != !d_aff) || (N && !pts && !aff))
+    return fail(ctx, MH_EINVAL, "mh_upload_correspondences: bad arguments");
   if (N == 0) return MH_OK;
   const uint64_t bytes = sizeof(double) * 4 * (uint64_t)N;
   MH_TRY(ensure_staging(ctx, 2 * bytes));
   double* raw_p = (double*)ctx->staging;
   double* raw_a = raw_p + 4 * N;
-  MH_CUDA(ctx, cudaMemcpyAsync(raw_p, pts, bytes, cudaMemcpyHostToDevice, ctx->stream));
-  if (d_aff) MH_CUDA(ctx, cudaMemcpyAsync(raw_a, aff, bytes, cudaMemcpyHostToDevice, ctx->stream));
-  return launch_normalize_points(ctx, raw_p, d_aff ? raw_a : nullptr, N, (float4*)d_pts, (float4*)d_aff);
+  if (pts) MH_CUDA(ctx, cudaMemcpyAsync(raw_p, pts, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  if (aff) MH_CUDA(ctx, cudaMemcpyAsync(raw_a, aff, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  return launch_normalize_points(ctx, pts ? raw_p : nullptr, aff ? raw_a : nullptr, N, (float4*)d_pts, (float4*)d_aff);
 }
 
 mh_status mh_hypotheses_from_host(mh_ctx* ctx, const double* H, int32_t K, void* d_hyp) {
@@ -438,7 +441,7 @@ mh_status mh_meanshift(mh_ctx* ctx, const void* d_feat, int32_t N, int32_t D, do
     return fail(ctx, MH_EINVAL, "mh_meanshift: bad arguments");
   *C_out = 0;
   if (N == 0) return MH_OK;
-  return launch_meanshift(ctx, (const double*)d_feat, N, D, bw, ctx->params.meanshift_metric, &ctx->params.rng_seed,
+  return launch_meanshift(ctx, (const double*)d_feat, N, D, bw, ctx->params.meanshift_metric, &ctx->rng_state,
                           (double*)d_centres, max_c, (int32_t*)d_assign, C_out, stats);
 }
 
@@ -476,6 +479,13 @@ mh_status mh_modes_to_hypotheses(mh_ctx* ctx, const void* d_modes, int32_t C, vo
   if (C < 0 || (C && (!d_modes || !d_hyp))) return fail(ctx, MH_EINVAL, "mh_modes_to_hypotheses: bad arguments");
   return launch_modes_to_hyp(ctx, (const double*)d_modes, C, (float*)d_hyp);
 }
+
+mh_status mh_set_rng_state(mh_ctx* ctx, uint32_t state) {
+  if (!ctx) return MH_EINVAL;
+  ctx->rng_state = state;
+  return MH_OK;
+}
+uint32_t mh_get_rng_state(const mh_ctx* ctx) { return ctx ? ctx->rng_state : 0u; }
 
 double mh_get_energy(const mh_ctx* ctx) { return ctx ? ctx->energy : 0.0; }
 int32_t mh_get_iterations(const mh_ctx* ctx) { return ctx ? ctx->iterations : 0; }

@@ -51,6 +51,7 @@ struct mh_ctx {
   double e2_px[2];
   std::string err;
   int64_t launches = 0;
+  uint32_t rng_state = 1u;  // state of the restated MSVC rand() (MS.h:54); mh_process re-seeds it from params.rng_seed
   // grow-only scratch arena (device) + pinned staging (host)
   void* scratch = nullptr;
   uint64_t scratch_bytes = 0;

@@ -23,10 +23,12 @@ __global__ void normalize_points_kernel(const double* __restrict__ pts_raw, cons
                                         long long N, float4* __restrict__ pts, float4* __restrict__ aff, HafGeom g) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N) return;
-  const double2* p = reinterpret_cast<const double2*>(pts_raw + 4 * i);
-  const double2 a = p[0], b = p[1];
-  pts[i] = make_float4((float)(a.x * g.s1 + g.t1x), (float)(a.y * g.s1 + g.t1y), (float)(b.x * g.s2 + g.t2x),
-                       (float)(b.y * g.s2 + g.t2y));
+  if (pts_raw && pts) {
+    const double2* p = reinterpret_cast<const double2*>(pts_raw + 4 * i);
+    const double2 a = p[0], b = p[1];
+    pts[i] = make_float4((float)(a.x * g.s1 + g.t1x), (float)(a.y * g.s1 + g.t1y), (float)(b.x * g.s2 + g.t2x),
+                         (float)(b.y * g.s2 + g.t2y));
+  }
   if (aff_raw && aff) {
     const double2* q = reinterpret_cast<const double2*>(aff_raw + 4 * i);
     const double2 c = q[0], d = q[1];

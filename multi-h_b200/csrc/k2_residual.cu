@@ -477,6 +477,176 @@ cost_argmin_kernel(const float4* __restrict__ pts, long long N, const float* __r
   }
 }
 
+// ----------------------------------------------------------------------------
+// v4 "transposed" register tile: each thread keeps HP hypothesis PAIRS in registers (18 regs per pair) and the CTA's
+// correspondence tile lives in shared memory, read with warp-uniform (broadcast) LDS — per correspondence one LDS.128
+// of (x, y, -x2, -y2) and one LDS.128 of its mutable argmin filter (-mid, half, mid - thr2).  Compared with v3 this
+// makes the per-hypothesis inlier counters thread-private (no REDUX / shared atomics in the loop: sign bits are
+// funnel-shifted into a 32-correspondence mask and POPCed once per 32 correspondences) and keeps every FFMA2 operand in
+// ordinary registers (no R2UR traffic).  The per-correspondence argmin state is shared by the CTA instead: a candidate
+// that passes the folded interval test recomputes its exact cost, the warp REDUX.MINs (cost << 16 | label) over its
+// candidate lanes, and one lane atomicMins the shared best and publishes the tightened filter with a single STS.128.
+// A reader may see a filter that is one update old — always the looser one, so no candidate is ever missed; the exact
+// integer compare rejects the false positives.  Per residual: 5 FFMA2 + 0.5 FADD2 + 1 MUFU + 1 SHF + 0.5 FMNMX +
+// 0.5 FSETP + 2/(2 HP) LDS.
+// ----------------------------------------------------------------------------
+// hypotheses [K][12] -> pair-interleaved [ceil(K/2)][10] 64-bit words {h_k(a), h_k(b)} (k = 0..8, + pad), so that a thread
+// loads its register-resident pairs with 128-bit loads and every FFMA2 operand is born as an aligned register pair.
+// Out-of-range hypotheses become "far" (residual ~1e36, never a hit).
+__global__ void pack_hyp_pairs_kernel(const float* __restrict__ hyp, int K, int npairs, u64* __restrict__ out) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= npairs) return;
+  float a[9], b[9];
+#pragma unroll
+  for (int e = 0; e < 2; ++e) {
+    float* d = e ? b : a;
+    const int ih = 2 * j + e;
+    if (ih < K) {
+      const float4* p = reinterpret_cast<const float4*>(hyp + (size_t)ih * 12);
+      const float4 u = p[0], v = p[1], w = p[2];
+      d[0] = u.x; d[1] = u.y; d[2] = u.z; d[3] = u.w; d[4] = v.x; d[5] = v.y; d[6] = v.z; d[7] = v.w; d[8] = w.x;
+    } else {
+      d[0] = d[1] = d[3] = d[4] = d[6] = d[7] = 0.f; d[2] = d[5] = 1e18f; d[8] = 1.f;
+    }
+  }
+  u64* o = out + (size_t)j * 10;
+#pragma unroll
+  for (int k = 0; k < 9; ++k) o[k] = pk(a[k], b[k]);
+  o[9] = 0ull;
+}
+
+template <bool COUNT_INLIERS, int THREADS, int MINB, int HP, int PT>
+__global__ void __launch_bounds__(THREADS, MINB)
+cost_argmin_t_kernel(const float4* __restrict__ pts, long long N, const u64* __restrict__ hyp_pairs, int K, int k_per_block,
+                     CostParams cp, FastOut o, int use_atomic_best) {
+  __shared__ __align__(16) float4 s_pt[PT];      // x, y, -x2, -y2
+  __shared__ __align__(16) float4 s_flt[PT];     // -mid, half, mid - thr2, unused
+  __shared__ unsigned s_best[PT];                // cost << 16 | label  (label 0 = outlier at the outlier cost)
+  static_assert(PT % 32 == 0, "tile must be a multiple of 32 correspondences");
+  constexpr int HYP_PER_THREAD = 2 * HP, HYP_PER_BLOCK = THREADS * HYP_PER_THREAD;
+
+  const long long tile0 = (long long)blockIdx.x * PT;
+  const int kbeg = blockIdx.y * k_per_block;
+  const int kend = min(K, kbeg + k_per_block);
+  const unsigned best_init = ((unsigned)min(cp.cost_outlier, 0xffff) << 16);
+
+  for (int i = threadIdx.x; i < PT; i += THREADS) {
+    const long long idx = tile0 + i;
+    const float4 q = pts[idx < N ? idx : N - 1];
+    float negmid, half;
+    fast_thresholds(cp.cost_outlier, cp, negmid, half);
+    float c = -negmid - cp.thr2;
+    if (idx >= N) { half = -1.f; c = 3.0e38f; }  // padding: never an inlier, never a candidate
+    s_pt[i] = make_float4(q.x, q.y, -q.z, -q.w);
+    s_flt[i] = make_float4(negmid, half, c, 0.f);
+    s_best[i] = best_init;
+  }
+  __syncthreads();
+  const u64 ONE2 = pk(1.f, 1.f);
+
+  for (int hb = kbeg; hb < kend; hb += HYP_PER_BLOCK) {
+    // this thread's hypothesis pairs -> registers, as aligned 64-bit pairs straight from the packed array
+    u64 H[HP][9];
+    const int h0 = hb + threadIdx.x * HYP_PER_THREAD;
+#pragma unroll
+    for (int q = 0; q < HP; ++q) {
+      const int jp = min((h0 >> 1) + q, (K + 1) / 2 - 1);  // clamp: pairs past the end are never counted (labels >= kend)
+      const ulonglong2* hp = reinterpret_cast<const ulonglong2*>(hyp_pairs + (size_t)jp * 10);
+      const ulonglong2 q0 = hp[0], q1 = hp[1], q2 = hp[2], q3 = hp[3], q4 = hp[4];
+      H[q][0] = q0.x; H[q][1] = q0.y; H[q][2] = q1.x; H[q][3] = q1.y; H[q][4] = q2.x;
+      H[q][5] = q2.y; H[q][6] = q3.x; H[q][7] = q3.y; H[q][8] = q4.x;
+    }
+    const bool live_pair0 = true;
+    (void)live_pair0;
+    int cnt[HYP_PER_THREAD];
+#pragma unroll
+    for (int h = 0; h < HYP_PER_THREAD; ++h) cnt[h] = 0;
+
+#pragma unroll 1
+    for (int i0 = 0; i0 < PT; i0 += 32) {
+      unsigned mask[HYP_PER_THREAD];
+#pragma unroll
+      for (int h = 0; h < HYP_PER_THREAD; ++h) mask[h] = 0u;
+#pragma unroll 2
+      for (int ii = 0; ii < 32; ++ii) {
+        const int i = i0 + ii;
+        const float4 P = s_pt[i];
+        const float4 Fl = s_flt[i];
+        const u64 xx = pk(P.x, P.x), yy = pk(P.y, P.y), nx2 = pk(P.z, P.z), ny2 = pk(P.w, P.w);
+        const u64 negmid = pk(Fl.x, Fl.x), cc = pk(Fl.z, Fl.z);
+        bool any = false;
+#pragma unroll
+        for (int q = 0; q < HP; ++q) {
+          const u64 sv = fma2(H[q][6], xx, fma2(H[q][7], yy, H[q][8]));
+          const u64 xn = fma2(H[q][0], xx, fma2(H[q][1], yy, H[q][2]));
+          const u64 yn = fma2(H[q][3], xx, fma2(H[q][4], yy, H[q][5]));
+          float sl, sh;
+          upk(sv, sl, sh);
+          const u64 r = pk(rcp_approx(sl), rcp_approx(sh));
+          const u64 dx = fma2(xn, r, nx2);
+          const u64 dy = fma2(yn, r, ny2);
+          const u64 t = fma2(dx, dx, fma2(dy, dy, negmid));  // d2 - mid
+          float ta, tb;
+          upk(t, ta, tb);
+          if (COUNT_INLIERS) {
+            float va, vb;
+            upk(fma2(t, ONE2, cc), va, vb);  // d2 - thr2: the sign bit is the inlier flag
+            mask[2 * q] = __funnelshift_l(__float_as_uint(va), mask[2 * q], 1);
+            mask[2 * q + 1] = __funnelshift_l(__float_as_uint(vb), mask[2 * q + 1], 1);
+          }
+          any = any || (fminf(fabsf(ta), fabsf(tb)) < Fl.y);
+        }
+        if (any) {  // some lane holds a candidate for correspondence i: exact update
+          unsigned mine = 0xffffffffu;
+#pragma unroll
+          for (int q = 0; q < HP; ++q) {
+            float ha[9], hb2[9];
+#pragma unroll
+            for (int k = 0; k < 9; ++k) upk(H[q][k], ha[k], hb2[k]);
+            const float da = residual(ha, P.x, P.y, -P.z, -P.w);
+            const float db = residual(hb2, P.x, P.y, -P.z, -P.w);
+            const unsigned la = (unsigned)(h0 + 2 * q + 1);  // 1-based label of lane a
+            if (da < cp.T && (int)la <= kend) mine = min(mine, ((unsigned)cost_in_range(da, cp) << 16) | la);
+            if (db < cp.T && (int)la + 1 <= kend) mine = min(mine, ((unsigned)cost_in_range(db, cp) << 16) | (la + 1));
+          }
+          const unsigned act = __activemask();
+          const unsigned wbest = __reduce_min_sync(act, mine);
+          if (mine == wbest && wbest < s_best[i]) {  // at most one lane per distinct value; ties carry the same value
+            const unsigned old = atomicMin(&s_best[i], wbest);
+            const unsigned now = min(old, wbest);
+            float nm, hf;
+            // hypotheses arrive in no particular label order here, so an equal-cost candidate with a LOWER label must
+            // still get through (GCO keeps the first label among equal costs): filter on cost <= best, not < best
+            fast_thresholds((int)(now >> 16) + 1, cp, nm, hf);
+            if (tile0 + i < N) s_flt[i] = make_float4(nm, hf, -nm - cp.thr2, 0.f);
+          }
+        }
+      }
+      if (COUNT_INLIERS) {
+#pragma unroll
+        for (int h = 0; h < HYP_PER_THREAD; ++h) cnt[h] += __popc(mask[h]);
+      }
+    }
+    if (COUNT_INLIERS) {
+#pragma unroll
+      for (int h = 0; h < HYP_PER_THREAD; ++h)
+        if (cnt[h] && h0 + h < kend) atomicAdd(o.inlier_count + h0 + h, cnt[h]);
+    }
+  }
+  __syncthreads();
+  if (o.best) {
+    for (int i = threadIdx.x; i < PT; i += THREADS) {
+      const long long idx = tile0 + i;
+      const unsigned b = s_best[i];
+      if (idx < N && (b & 0xffffu) != 0u) {
+        const u64 v = ((u64)(b >> 16) << 32) | (u64)(b & 0xffffu);
+        if (use_atomic_best) atomicMin(o.best + idx, v);
+        else o.best[idx] = v;
+      }
+    }
+  }
+}
+
 __global__ void fused_init_kernel(long long N, int K, int32_t* list_count, u64* best, int32_t* inlier_count,
                                   u64 best_init) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -531,7 +701,32 @@ mh_status launch_cost_fused(mh_ctx* ctx, const float4* d_pts, int64_t N, const f
       else kernel_nocnt<<<gridf, threads, 0, ctx->stream>>>(d_pts, N, d_hyp, K, kpb, cp, fo, ks > 1);
       return MH_OK;
     };
+    auto launch_t = [&](auto kernel_cnt, auto kernel_nocnt, int threads, int hyp_per_block, int pt) -> mh_status {
+      const int npairs = (K + 1) / 2;
+      MH_TRY(ensure_scratch(ctx, sizeof(u64) * 10 * (uint64_t)npairs));
+      u64* d_pairs = (u64*)ctx->scratch;
+      pack_hyp_pairs_kernel<<<(unsigned)((npairs + 127) / 128), 128, 0, ctx->stream>>>(d_hyp, K, npairs, d_pairs);
+      MH_LAUNCHED(ctx, "pack_hyp_pairs_kernel");
+      const unsigned tiles_f = (unsigned)((N + pt - 1) / pt);
+      int ks = 1;
+      if ((int)tiles_f < want) ks = std::min((K + hyp_per_block - 1) / hyp_per_block, (want + (int)tiles_f - 1) / (int)tiles_f);
+      ks = std::max(1, ks);
+      int kpb = (K + ks - 1) / ks;
+      kpb = ((kpb + hyp_per_block - 1) / hyp_per_block) * hyp_per_block;  // whole hypothesis blocks per CTA
+      ks = (K + kpb - 1) / kpb;
+      dim3 gridf(tiles_f, (unsigned)ks);
+      if (cnt) kernel_cnt<<<gridf, threads, 0, ctx->stream>>>(d_pts, N, d_pairs, K, kpb, cp, fo, ks > 1);
+      else kernel_nocnt<<<gridf, threads, 0, ctx->stream>>>(d_pts, N, d_pairs, K, kpb, cp, fo, ks > 1);
+      return MH_OK;
+    };
+    if (K >= 65535 || cp.cost_outlier > 0xffff) g_fast_config = std::min(g_fast_config, 6);  // v4 packs (cost, label) in 32 bits
     switch (g_fast_config) {
+      case 10: launch_t(cost_argmin_t_kernel<true, 128, 6, 2, 512>, cost_argmin_t_kernel<false, 128, 6, 2, 512>, 128, 512, 512); break;
+      case 11: launch_t(cost_argmin_t_kernel<true, 128, 5, 2, 512>, cost_argmin_t_kernel<false, 128, 5, 2, 512>, 128, 512, 512); break;
+      case 12: launch_t(cost_argmin_t_kernel<true, 128, 4, 4, 512>, cost_argmin_t_kernel<false, 128, 4, 4, 512>, 128, 1024, 512); break;
+      case 13: launch_t(cost_argmin_t_kernel<true, 128, 3, 4, 512>, cost_argmin_t_kernel<false, 128, 3, 4, 512>, 128, 1024, 512); break;
+      case 14: launch_t(cost_argmin_t_kernel<true, 256, 3, 2, 1024>, cost_argmin_t_kernel<false, 256, 3, 2, 1024>, 256, 1024, 1024); break;
+      case 15: launch_t(cost_argmin_t_kernel<true, 128, 7, 2, 256>, cost_argmin_t_kernel<false, 128, 7, 2, 256>, 128, 512, 256); break;
       case 0: launch(cost_argmin_kernel<true, 256, 3, 256>, cost_argmin_kernel<false, 256, 3, 256>, 256, 256); break;
       case 1: launch(cost_argmin_kernel<true, 256, 2, 256>, cost_argmin_kernel<false, 256, 2, 256>, 256, 256); break;
       case 3: launch(cost_argmin_kernel<true, 128, 5, 256>, cost_argmin_kernel<false, 128, 5, 256>, 128, 256); break;

@@ -78,6 +78,7 @@ mh_status mh_process(mh_ctx* ctx, const double* pts, const double* aff, const do
   // normalised data path (the throughput kernels) — same control flow, results equal up to FP32 rounding.
   const bool precise = P.precise_pipeline != 0;
   const double t_start = now_ms();
+  ctx->rng_state = P.rng_seed;  // every Process() call starts from the same generator state, like a fresh run of the reference
   MH_TRY(mh_set_geometry(ctx, F, nullptr, nullptr, pts, N));
 
   DevBuf b_pts, b_aff, b_pts64, b_aff64, b_hyp_pt, b_hyp_pt64, b_feat, b_centres, b_assign, b_hyp, b_hyp64, b_keep, b_cost,

@@ -27,7 +27,7 @@ f10g = ctx.features10(ctx.haf_hypotheses(d_pts, d_aff), d_pts).cpu().numpy()
 print("feat10 abs p99/max", np.percentile(np.abs(f10 - f10g).max(1), 99), np.abs(f10 - f10g).max())
 rng = 1
 centres, assign, rng_o, st_o = orc.meanshift(f10, thr, 0, rng)
-ctx.params.rng_seed = 1
+ctx.rng_state = 1
 cg, ag, st_g = ctx.meanshift(torch.from_numpy(f10).cuda(), thr)
 print("MS10 same-features: stats", st_g, st_o, "C", cg.shape[0], len(centres), "assign agree", (ag.cpu().numpy() == assign).mean())
 ctx2 = m.Context(m.capi.default_params(locality=locality)); ctx2.set_geometry(F, pts)
@@ -49,9 +49,9 @@ for it in range(1, 60):
     d_hyp = ctx.hypotheses_from_host(hyp)
     f6g = ctx.features6(d_hyp).cpu().numpy()
     modes, _, rng2, st = orc.meanshift(f6, thr, 0, rng)
-    ctx.params.rng_seed = rng
+    ctx.rng_state = rng
     mg, _, stg = ctx.meanshift(torch.from_numpy(f6).cuda(), thr)
-    ctx.params.rng_seed = rng
+    ctx.rng_state = rng
     mg2, _, stg2 = ctx.meanshift(torch.from_numpy(f6g).cuda(), thr)
     rng = rng2
     Hm = np.stack([orc.mode_to_homography(mo, F).ravel() for mo in modes])
