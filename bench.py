@@ -10,9 +10,8 @@ One "step" = one pass of the hot path over the scene:
     [N>1] NCCL broadcast of the 8192 x 12 hypothesis block from rank 0
     K2  fused N x K residual / data cost: per-site data-term argmin label + cost and per-hypothesis inlier
         count — nothing N x K touches HBM (MultiH.cpp:473-504, 430-443, 743-768)
-    [N>1] NCCL all-reduce of the K inlier counts
     K4  per-label refit statistics from the argmin labels (segmented reduction of SUM A^T A)
-    [N>1] NCCL all-reduce of the K x 12 FP64 statistics
+    [N>1] ONE NCCL all-reduce of the K x 12 FP64 statistics (inlier counts ride in the pad column)
     K4  batched 4x4 eigen-solves -> refined homographies      (MultiH.cpp:545-599, 913-990)
 `value` times that with the inputs resident in HBM; `e2e` times the same pass through the C ABI from PINNED HOST
 buffers (H2D of the FP64 correspondences + affines, normalisation, the pass, D2H of labels + refined homographies).
@@ -181,6 +180,17 @@ def main():
     k2_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
              for _ in range(args.steps + args.warmup + 1)]
 
+    def stats_and_refit():
+        """K2 outputs -> labels -> K4 statistics; ONE all-reduce carries refit statistics + inlier counts"""
+        ctx.labels_from_best(fused["best"], labels)                                          # -1 = outlier
+        d_ref.copy_(d_hyp)
+        ctx.refit_haf_accumulate(d_pts, d_aff, labels, K_HYP, out=acc)                       # K4 statistics
+        if world > 1:
+            ctx.pack_inlier_counts(fused["inliers"], acc)
+            dist.all_reduce(acc)
+            ctx.pack_inlier_counts(fused["inliers"], acc, unpack=True)
+        ctx.refit_haf_solve(acc, d_ref)                                                      # K4 solves
+
     def hot_pass(ev=None):
         ctx.haf_hypotheses(d_pts, d_aff, out=d_hyp_pt)                                      # K1
         if world > 1:
@@ -190,15 +200,7 @@ def main():
         ctx.data_cost_fused(d_pts, d_hyp, kmax=0, want_list=False, out=fused)                # K2
         if ev is not None:
             ev[1].record()
-        if world > 1:
-            dist.all_reduce(fused["inliers"])
-        torch.bitwise_and(fused["best"], 0xFFFFFFFF, out=fused["best"])                      # label = low word
-        labels.copy_(fused["best"]); labels.sub_(1)                                          # -1 = outlier
-        d_ref.copy_(d_hyp)
-        ctx.refit_haf_accumulate(d_pts, d_aff, labels, K_HYP, out=acc)                       # K4 statistics
-        if world > 1:
-            dist.all_reduce(acc)
-        ctx.refit_haf_solve(acc, d_ref)                                                      # K4 solves
+        stats_and_refit()
 
     # end-to-end: the two host->device uploads run on their own stream (second context = second stream, same geometry);
     # K2 needs only the points, so it starts as soon as they have landed and hides the upload of the affines.
@@ -216,17 +218,9 @@ def main():
             dist.broadcast(d_hyp, src=0)
         main.wait_event(ev_pts)
         ctx.data_cost_fused(d_pts, d_hyp, kmax=0, want_list=False, out=fused)                # K2
-        if world > 1:
-            dist.all_reduce(fused["inliers"])
         main.wait_event(ev_aff)
         ctx.haf_hypotheses(d_pts, d_aff, out=d_hyp_pt)                                      # K1
-        torch.bitwise_and(fused["best"], 0xFFFFFFFF, out=fused["best"])
-        labels.copy_(fused["best"]); labels.sub_(1)
-        d_ref.copy_(d_hyp)
-        ctx.refit_haf_accumulate(d_pts, d_aff, labels, K_HYP, out=acc)                       # K4
-        if world > 1:
-            dist.all_reduce(acc)
-        ctx.refit_haf_solve(acc, d_ref)
+        stats_and_refit()                                                                    # K4 (+ all-reduce)
         h_labels.copy_(labels, non_blocking=True)                                            # D2H results
         h_ref.copy_(d_ref, non_blocking=True)
         torch.cuda.synchronize()

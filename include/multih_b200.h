@@ -162,6 +162,11 @@ mh_status mh_refit_haf(mh_ctx* ctx, const void* d_pts, const void* d_aff, const 
 mh_status mh_refit_haf_accumulate(mh_ctx* ctx, const void* d_pts, const void* d_aff, const void* d_labels, int64_t N,
                                   int32_t K, void* d_acc);
 mh_status mh_refit_haf_solve(mh_ctx* ctx, const void* d_acc, int32_t K, void* d_hyp, void* d_count);
+/* Glue between K2 and K4 on the device: d_labels[i] = (d_best[i] & 0xffffffff) - 1 (the per-site argmin of
+ * mh_data_cost_fused as the -1..K-1 label array of MultiH.h:61-62); and (un)packing of the per-hypothesis inlier counts
+ * into the pad column d_acc[k][11], so that one all-reduce carries both statistics of a correspondence shard. */
+mh_status mh_labels_from_best(mh_ctx* ctx, const void* d_best, int64_t N, void* d_labels);
+mh_status mh_pack_inlier_counts(mh_ctx* ctx, void* d_inlier_count, int32_t K, void* d_acc, int32_t unpack);
 /* GetHomography3PT (MultiH.cpp:995-1055, linear solution) per cluster of EstablishStablePointSets (:664-688):
  * d_assign i32 [N] in -1..C-1; clusters with < 3 members get keep=0 (:667). */
 mh_status mh_refit_3pt(mh_ctx* ctx, const void* d_pts, const void* d_assign, int64_t N, int32_t C, void* d_hyp,

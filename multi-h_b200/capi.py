@@ -26,7 +26,7 @@ SYMBOLS = [
     "mh_set_geometry", "mh_get_geometry", "mh_upload_correspondences", "mh_hypotheses_from_host",
     "mh_hypotheses_to_host", "mh_haf_hypotheses", "mh_data_cost_dense", "mh_residuals", "mh_data_cost_fused",
     "mh_inlier_stats", "mh_inliers_of_homography", "mh_features10", "mh_features6", "mh_set_rng_state", "mh_get_rng_state", "mh_meanshift", "mh_refit_haf",
-    "mh_refit_haf_accumulate", "mh_refit_haf_solve", "mh_refit_3pt", "mh_modes_to_hypotheses", "mh_neighbourhood", "mh_alpha_expansion", "mh_process", "mh_get_energy",
+    "mh_refit_haf_accumulate", "mh_refit_haf_solve", "mh_labels_from_best", "mh_pack_inlier_counts", "mh_refit_3pt", "mh_modes_to_hypotheses", "mh_neighbourhood", "mh_alpha_expansion", "mh_process", "mh_get_energy",
     "mh_get_iterations", "mh_get_stage_ms", "mh_diag_fp32_peak", "mh_diag_set_fused_variant", "mh_diag_set_fast_config",
 ]
 
@@ -341,6 +341,13 @@ class Context:
         self._check(lib().mh_refit_haf_accumulate(self._h, _vp(d_pts), _vp(d_aff), _vp(d_labels),
                                                   C.c_int64(d_pts.shape[0]), int(K), _vp(acc)))
         return acc
+
+    def labels_from_best(self, d_best, d_labels):
+        self._check(lib().mh_labels_from_best(self._h, _vp(d_best), C.c_int64(d_best.shape[0]), _vp(d_labels)))
+        return d_labels
+
+    def pack_inlier_counts(self, d_cnt, d_acc, unpack=False):
+        self._check(lib().mh_pack_inlier_counts(self._h, _vp(d_cnt), int(d_cnt.shape[0]), _vp(d_acc), int(unpack)))
 
     def refit_haf_solve(self, d_acc, d_hyp, d_count=None):
         self._check(lib().mh_refit_haf_solve(self._h, _vp(d_acc), int(d_acc.shape[0]), _vp(d_hyp), _vp(d_count)))

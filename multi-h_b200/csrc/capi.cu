@@ -467,6 +467,18 @@ mh_status mh_refit_haf_solve(mh_ctx* ctx, const void* d_acc, int32_t K, void* d_
   return launch_refit_haf_solve(ctx, (const double*)d_acc, K, (float*)d_hyp, (int32_t*)d_count);
 }
 
+mh_status mh_labels_from_best(mh_ctx* ctx, const void* d_best, int64_t N, void* d_labels) {
+  if (!ctx) return MH_EINVAL;
+  if (N < 0 || (N && (!d_best || !d_labels))) return fail(ctx, MH_EINVAL, "mh_labels_from_best: bad arguments");
+  return launch_labels_from_best(ctx, (const unsigned long long*)d_best, N, (int32_t*)d_labels);
+}
+
+mh_status mh_pack_inlier_counts(mh_ctx* ctx, void* d_inlier_count, int32_t K, void* d_acc, int32_t unpack) {
+  if (!ctx) return MH_EINVAL;
+  if (K < 0 || (K && (!d_inlier_count || !d_acc))) return fail(ctx, MH_EINVAL, "mh_pack_inlier_counts: bad arguments");
+  return launch_pack_inlier_counts(ctx, (int32_t*)d_inlier_count, K, (double*)d_acc, unpack);
+}
+
 mh_status mh_refit_3pt(mh_ctx* ctx, const void* d_pts, const void* d_assign, int64_t N, int32_t C, void* d_hyp,
                        void* d_keep) {
   NEED_GEOM(ctx);

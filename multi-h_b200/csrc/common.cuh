@@ -124,6 +124,8 @@ mh_status launch_refit_haf_accumulate(mh_ctx*, const float4* d_pts, const float4
                                       const double* d_aff64 = nullptr);
 mh_status launch_refit_haf_solve(mh_ctx*, const double* d_acc, int K, float* d_hyp, int32_t* d_count,
                                  double* d_hyp64 = nullptr);
+mh_status launch_labels_from_best(mh_ctx*, const unsigned long long* d_best, int64_t N, int32_t* d_labels);
+mh_status launch_pack_inlier_counts(mh_ctx*, int32_t* d_cnt, int K, double* d_acc, int unpack);
 mh_status launch_refit_3pt(mh_ctx*, const float4* d_pts, const int32_t* d_assign, int64_t N, int C, float* d_hyp,
                            int32_t* d_keep, const double* d_pts64 = nullptr, double* d_hyp64 = nullptr);
 mh_status launch_modes_to_hyp(mh_ctx*, const double* d_modes, int C, float* d_hyp, double* d_hyp64 = nullptr);

@@ -209,6 +209,35 @@ __global__ void haf_solve_kernel(const double* __restrict__ acc, int K, float* _
   haf_store(v, g, false, hyp + 12 * (size_t)l, hyp64 ? hyp64 + 9 * (size_t)l : nullptr);  // no division by h33 (MultiH.cpp:977-989)
 }
 
+// label_i = (best_i & 0xffffffff) - 1  (-1 = outlier): the argmin output of K2 as the label array K4 consumes
+__global__ void labels_from_best_kernel(const unsigned long long* __restrict__ best, long long N, int32_t* __restrict__ labels) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < N) labels[i] = (int32_t)(best[i] & 0xffffffffull) - 1;
+}
+// acc[k][11] = inlier count of hypothesis k, so that ONE all-reduce carries the refit statistics and the inlier counts
+__global__ void pack_inlier_counts_kernel(const int32_t* __restrict__ cnt, int K, double* __restrict__ acc) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < K) acc[12 * (size_t)k + 11] = (double)cnt[k];
+}
+__global__ void unpack_inlier_counts_kernel(const double* __restrict__ acc, int K, int32_t* __restrict__ cnt) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < K) cnt[k] = (int32_t)(acc[12 * (size_t)k + 11] + 0.5);
+}
+
+mh_status launch_labels_from_best(mh_ctx* ctx, const unsigned long long* d_best, int64_t N, int32_t* d_labels) {
+  if (N <= 0) return MH_OK;
+  labels_from_best_kernel<<<(unsigned)((N + 255) / 256), 256, 0, ctx->stream>>>(d_best, N, d_labels);
+  MH_LAUNCHED(ctx, "labels_from_best_kernel");
+  return MH_OK;
+}
+mh_status launch_pack_inlier_counts(mh_ctx* ctx, int32_t* d_cnt, int K, double* d_acc, int unpack) {
+  if (K <= 0) return MH_OK;
+  if (unpack) unpack_inlier_counts_kernel<<<(unsigned)((K + 255) / 256), 256, 0, ctx->stream>>>(d_acc, K, d_cnt);
+  else pack_inlier_counts_kernel<<<(unsigned)((K + 255) / 256), 256, 0, ctx->stream>>>(d_cnt, K, d_acc);
+  MH_LAUNCHED(ctx, "pack_inlier_counts_kernel");
+  return MH_OK;
+}
+
 mh_status launch_refit_haf_accumulate(mh_ctx* ctx, const float4* d_pts, const float4* d_aff, const int32_t* d_labels,
                                       int64_t N, int K, double* d_acc, const double* d_pts64, const double* d_aff64) {
   if (K <= 0) return MH_OK;
