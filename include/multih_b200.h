@@ -102,6 +102,17 @@ mh_status mh_hypotheses_from_host(mh_ctx* ctx, const double* H_host /*K x 9 px*/
 mh_status mh_hypotheses_to_host(mh_ctx* ctx, const void* d_hyp, int32_t K, double* H_host /*K x 9 px*/,
                                 int32_t divide_by_h33);
 
+/* ---- K0: per-correspondence pre-filter (the step directly before K1) ------------
+ * The refinement loop of GetFundamentalMatrixAndRefineData with F given (MultiH.cpp:786-838): OptimalTriangulation
+ * (:1116-1188), GetAffineConsistency / GetBetaScale (:1057-1114, drop when distanceError > 1), GetOptimalAffineTransformation
+ * (:1190-1223).  FP64 pixels in, survivors out in input order (the reference's push_back order); keep_host (N bytes,
+ * optional) flags the survivors; *M_out = their number.  The RANSAC estimation of F itself (MultiH.cpp:775) stays upstream. */
+mh_status mh_prefilter(mh_ctx* ctx, const double* pts_host, const double* aff_host, const double F[9], int64_t N,
+                       double* pts_out_host, double* aff_out_host, uint8_t* keep_host, int64_t* M_out);
+/* same on device-resident FP64 arrays (N x 4 each); d_keep i32 [N] */
+mh_status mh_prefilter_device(mh_ctx* ctx, const void* d_pts64, const void* d_aff64, const double F[9], int64_t N,
+                              void* d_pts64_out, void* d_aff64_out, void* d_keep, int64_t* M_out);
+
 /* ---- K1: per-correspondence HAF hypotheses ------------------------------
  * MultiH::ComputeLocalHomographies (MultiH.cpp:696-717) -> GetHomographyHAF (:850-911).
  * Solved in pixel coordinates in FP64 (A^T A + cyclic Jacobi, as the reference) — the least-squares estimate is not

@@ -24,7 +24,7 @@ SYMBOLS = [
     "mh_default_params", "mh_create", "mh_destroy", "mh_last_error", "mh_version", "mh_set_stream", "mh_sync",
     "mh_alloc", "mh_free", "mh_host_alloc", "mh_host_free", "mh_memcpy_d2h", "mh_memcpy_h2d", "mh_kernel_launches",
     "mh_set_geometry", "mh_get_geometry", "mh_upload_correspondences", "mh_hypotheses_from_host",
-    "mh_hypotheses_to_host", "mh_haf_hypotheses", "mh_data_cost_dense", "mh_residuals", "mh_data_cost_fused",
+    "mh_hypotheses_to_host", "mh_prefilter", "mh_prefilter_device", "mh_haf_hypotheses", "mh_data_cost_dense", "mh_residuals", "mh_data_cost_fused",
     "mh_inlier_stats", "mh_inliers_of_homography", "mh_features10", "mh_features6", "mh_set_rng_state", "mh_get_rng_state", "mh_meanshift", "mh_refit_haf",
     "mh_refit_haf_accumulate", "mh_refit_haf_solve", "mh_labels_from_best", "mh_pack_inlier_counts", "mh_refit_3pt", "mh_modes_to_hypotheses", "mh_neighbourhood", "mh_alpha_expansion", "mh_process", "mh_get_energy",
     "mh_get_iterations", "mh_get_stage_ms", "mh_diag_fp32_peak", "mh_diag_set_fused_variant", "mh_diag_set_fast_config",
@@ -238,6 +238,16 @@ class Context:
         H = np.zeros((K, 9))
         self._check(lib().mh_hypotheses_to_host(self._h, _vp(d_hyp), K, _p(H, C.c_double), int(divide_by_h33)))
         return H
+
+    # -- K0
+    def prefilter(self, pts, aff, F):
+        """mh_prefilter: MultiH.cpp:786-838 with F given. Returns (pts_kept, aff_kept, keep mask)."""
+        pts = _np(pts, np.float64); aff = _np(aff, np.float64); F = _np(F, np.float64).reshape(9)
+        N = pts.shape[0]
+        po = np.zeros((N, 4)); ao = np.zeros((N, 4)); keep = np.zeros(N, dtype=np.uint8); M = C.c_int64(0)
+        self._check(lib().mh_prefilter(self._h, _p(pts, C.c_double), _p(aff, C.c_double), _p(F, C.c_double), C.c_int64(N),
+                                       _p(po, C.c_double), _p(ao, C.c_double), _p(keep, C.c_uint8), C.byref(M)))
+        return po[: M.value].copy(), ao[: M.value].copy(), keep.astype(bool)
 
     # -- K1
     def haf_hypotheses(self, d_pts, d_aff, precision=0, out=None):

@@ -348,6 +348,45 @@ mh_status mh_hypotheses_to_host(mh_ctx* ctx, const void* d_hyp, int32_t K, doubl
   return MH_OK;
 }
 
+mh_status mh_prefilter(mh_ctx* ctx, const double* pts, const double* aff, const double F[9], int64_t N, double* pts_out,
+                       double* aff_out, uint8_t* keep_out, int64_t* M_out) {
+  if (!ctx) return MH_EINVAL;
+  if (!F || !M_out || N < 0 || (N && (!pts || !aff || !pts_out || !aff_out))) return fail(ctx, MH_EINVAL, "mh_prefilter: bad arguments");
+  *M_out = 0;
+  if (N == 0) return MH_OK;
+  const uint64_t rows = sizeof(double) * 4 * (uint64_t)N;
+  MH_TRY(ensure_staging(ctx, 4 * rows + sizeof(int32_t) * (uint64_t)N));
+  double* d_p = (double*)ctx->staging;
+  double* d_a = d_p + 4 * N;
+  double* d_po = d_a + 4 * N;
+  double* d_ao = d_po + 4 * N;
+  int32_t* d_keep = (int32_t*)(d_ao + 4 * N);
+  MH_CUDA(ctx, cudaMemcpyAsync(d_p, pts, rows, cudaMemcpyHostToDevice, ctx->stream));
+  MH_CUDA(ctx, cudaMemcpyAsync(d_a, aff, rows, cudaMemcpyHostToDevice, ctx->stream));
+  int64_t M = 0;
+  MH_TRY(launch_prefilter(ctx, d_p, d_a, F, N, d_po, d_ao, d_keep, &M));
+  MH_CUDA(ctx, cudaMemcpyAsync(pts_out, d_po, sizeof(double) * 4 * (size_t)M, cudaMemcpyDeviceToHost, ctx->stream));
+  MH_CUDA(ctx, cudaMemcpyAsync(aff_out, d_ao, sizeof(double) * 4 * (size_t)M, cudaMemcpyDeviceToHost, ctx->stream));
+  std::vector<int32_t> k32;
+  if (keep_out) {
+    k32.resize(N);
+    MH_CUDA(ctx, cudaMemcpyAsync(k32.data(), d_keep, sizeof(int32_t) * (size_t)N, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  MH_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (keep_out) for (int64_t i = 0; i < N; ++i) keep_out[i] = (uint8_t)(k32[i] != 0);
+  *M_out = M;
+  return MH_OK;
+}
+
+mh_status mh_prefilter_device(mh_ctx* ctx, const void* d_pts64, const void* d_aff64, const double F[9], int64_t N,
+                              void* d_pts64_out, void* d_aff64_out, void* d_keep, int64_t* M_out) {
+  if (!ctx) return MH_EINVAL;
+  if (!F || !M_out || N < 0 || (N && (!d_pts64 || !d_aff64 || !d_pts64_out || !d_aff64_out || !d_keep)))
+    return fail(ctx, MH_EINVAL, "mh_prefilter_device: bad arguments");
+  return launch_prefilter(ctx, (const double*)d_pts64, (const double*)d_aff64, F, N, (double*)d_pts64_out, (double*)d_aff64_out,
+                          (int32_t*)d_keep, M_out);
+}
+
 mh_status mh_haf_hypotheses(mh_ctx* ctx, const void* d_pts, const void* d_aff, int64_t N, void* d_hyp, int32_t prec) {
   NEED_GEOM(ctx);
   if (N < 0 || (N && (!d_pts || !d_aff || !d_hyp))) return fail(ctx, MH_EINVAL, "mh_haf_hypotheses: bad arguments");

@@ -128,6 +128,8 @@ mh_status launch_labels_from_best(mh_ctx*, const unsigned long long* d_best, int
 mh_status launch_pack_inlier_counts(mh_ctx*, int32_t* d_cnt, int K, double* d_acc, int unpack);
 mh_status launch_refit_3pt(mh_ctx*, const float4* d_pts, const int32_t* d_assign, int64_t N, int C, float* d_hyp,
                            int32_t* d_keep, const double* d_pts64 = nullptr, double* d_hyp64 = nullptr);
+mh_status launch_prefilter(mh_ctx*, const double* d_pts64, const double* d_aff64, const double F[9], int64_t N,
+                           double* d_pts_out, double* d_aff_out, int32_t* d_keep, int64_t* M_out);
 mh_status launch_modes_to_hyp(mh_ctx*, const double* d_modes, int C, float* d_hyp, double* d_hyp64 = nullptr);
 // FP64 members of the K2 family for the precise path (small N x K only): dataEnergy, inlier scan, single-H inliers
 mh_status launch_cost_dense64(mh_ctx*, const double* d_pts64, int64_t N, const double* d_hyp64, int K, int32_t* d_cost);

@@ -676,3 +676,140 @@ int64_t orc_radius_neighbours(const double* pts, int N, double radius, int max_n
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------
+// Pre-path: the per-correspondence refinement loop of
+// MultiH::GetFundamentalMatrixAndRefineData (MH.cpp:786-838) with F given:
+// OptimalTriangulation (MH.cpp:1116-1188, Hartley-Sturm with the reference's
+// un-normalised epipole "rotations" MH.cpp:801-802), GetAffineConsistency
+// (:1057-1090, only distanceError is used, :826), GetBetaScale (:1092-1114) and
+// GetOptimalAffineTransformation (:1190-1223).  cv::solvePoly (OpenCV: Durand-
+// Kerner from the start values (1+i)^k, leading coefficients <= DBL_EPSILON
+// trimmed) is restated with a relative convergence test instead of OpenCV's
+// "until the update is exactly zero or 300*n sweeps".
+// keep[i] = 1 if the correspondence survives; out_pts/out_aff are written at
+// index i (not compacted) — the caller compacts in order, as the reference's
+// push_back does.
+// ---------------------------------------------------------------------------
+namespace {
+struct Cx { double re, im; };
+inline Cx cmul(Cx a, Cx b) { return {a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re}; }
+inline Cx cdiv(Cx a, Cx b) { const double d = b.re * b.re + b.im * b.im; return {(a.re * b.re + a.im * b.im) / d, (a.im * b.re - a.re * b.im) / d}; }
+int solve_poly_dk(const double* c /*ascending, 7*/, Cx* roots) {
+  int n = 6;
+  for (; n > 1; --n) if (std::fabs(c[n]) > DBL_EPSILON) break;
+  Cx p{1, 0}; const Cx r{1, 1};
+  for (int i = 0; i < n; ++i) { roots[i] = p; p = cmul(p, r); }
+  for (int iter = 0; iter < 300 * n; ++iter) {
+    double maxDiff = 0, maxRoot = 0;
+    for (int i = 0; i < n; ++i) {
+      p = roots[i];
+      Cx num{c[n], 0}, den{c[n], 0};
+      for (int j = 0; j < n; ++j) {
+        num = cmul(num, p); num.re += c[n - j - 1];
+        if (j != i) { Cx d{p.re - roots[j].re, p.im - roots[j].im}; if (d.re != 0 || d.im != 0) den = cmul(den, d); }
+      }
+      num = cdiv(num, den);
+      roots[i] = {p.re - num.re, p.im - num.im};
+      maxDiff = std::max(maxDiff, std::hypot(num.re, num.im));
+      maxRoot = std::max(maxRoot, std::hypot(roots[i].re, roots[i].im));
+    }
+    if (maxDiff <= 1e-16 * std::max(maxRoot, 1e-300)) break;
+  }
+  return n;
+}
+inline void mat3_inv(const double* m, double* o) {
+  const double a = m[0], b = m[1], c = m[2], d = m[3], e = m[4], f = m[5], g = m[6], h = m[7], i = m[8];
+  const double A = e * i - f * h, B = -(d * i - f * g), C = d * h - e * g, det = a * A + b * B + c * C;
+  o[0] = A / det; o[1] = -(b * i - c * h) / det; o[2] = (b * f - c * e) / det;
+  o[3] = B / det; o[4] = (a * i - c * g) / det; o[5] = -(a * f - c * d) / det;
+  o[6] = C / det; o[7] = -(a * h - b * g) / det; o[8] = (a * e - b * d) / det;
+}
+inline double beta_scale(const double* F, const double* p1, const double* p2) {  // MH.cpp:1092-1114
+  const double l1x = F[0] * p2[0] + F[3] * p2[1] + F[6], l1y = F[1] * p2[0] + F[4] * p2[1] + F[7], l1z = F[2] * p2[0] + F[5] * p2[1] + F[8];
+  const double l2x = F[0] * p1[0] + F[1] * p1[1] + F[2], l2y = F[3] * p1[0] + F[4] * p1[1] + F[5];
+  const double xn = p1[0] + 1.0, yn = -(l1x * xn + l1z) / l1y;
+  double dx = xn - p1[0], dy = yn - p1[1];
+  const double nn = std::sqrt(dx * dx + dy * dy);
+  dx /= nn; dy /= nn;
+  return std::fabs(std::sqrt(l2x * l2x + l2y * l2y) /
+                   ((-F[0] * dy + F[1] * dx) * p2[0] + (-F[3] * dy + F[4] * dx) * p2[1] - F[6] * dy + F[7] * dx));
+}
+}  // namespace
+
+extern "C" void orc_prefilter(const double* pts, const double* aff, const double* F, int64_t N, double* out_pts,
+                              double* out_aff, int32_t* keep) {
+  double e2[3], e1[3], Ft[9];
+  for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) Ft[i * 3 + j] = F[j * 3 + i];
+  epipole2(F, e2);   // MH.cpp:789-793
+  epipole2(Ft, e1);  // eigen(F^T F) last row / z, MH.cpp:795-799
+  const double R1[9] = {e1[0], e1[1], 0, -e1[1], e1[0], 0, 0, 0, 1};   // MH.cpp:801
+  const double R2[9] = {-e2[0], -e2[1], 0, e2[1], -e2[0], 0, 0, 0, 1}; // MH.cpp:802
+  const double f1 = 1.0, f2 = 1.0;  // epipoles are divided by z (MH.cpp:793, 799)
+  for (int64_t i = 0; i < N; ++i) {
+    keep[i] = 0;
+    const double p1[3] = {pts[4 * i], pts[4 * i + 1], 1.0}, p2[3] = {pts[4 * i + 2], pts[4 * i + 3], 1.0};
+    // ---- OptimalTriangulation (MH.cpp:1116-1188)
+    const double T1i[9] = {1, 0, p1[0], 0, 1, p1[1], 0, 0, 1};      // T1.inv()
+    const double T2ti[9] = {1, 0, 0, 0, 1, 0, p2[0], p2[1], 1};     // T2.t().inv()
+    double F2[9], F3[9], R1t[9];
+    mat3_mul(T2ti, F, F2); mat3_mul(F2, T1i, F2);
+    for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) R1t[r * 3 + c] = R1[c * 3 + r];
+    mat3_mul(R2, F2, F3); mat3_mul(F3, R1t, F3);
+    const double a = F3[4], b = F3[5], c = F3[7], d = F3[8];
+    const double f14 = f1 * f1 * f1 * f1, adbc = a * d - b * c;
+    double co[7];
+    co[6] = -a * c * f14 * adbc;
+    co[5] = (a * a + f2 * f2 * c * c) * (a * a + f2 * f2 * c * c) - (a * d + b * c) * f14 * adbc;
+    co[4] = 2 * (a * a + f2 * f2 * c * c) * (2 * a * b + 2 * c * d * f2 * f2) - d * b * f14 * adbc - 2 * a * c * f1 * f1 * adbc;
+    co[3] = (2 * a * b + 2 * c * d * f2 * f2) * (2 * a * b + 2 * c * d * f2 * f2) + 2 * (a * a + f2 * f2 * c * c) * (b * b + f2 * f2 * d * d) - 2 * f1 * f1 * adbc * (a * d + b * c);
+    co[2] = 2 * (2 * a * b + 2 * c * d * f2 * f2) * (b * b + f2 * f2 * d * d) - 2 * (f1 * f1 * a * d - f1 * f1 * b * c) * b * d - a * c * adbc;
+    co[1] = (b * b + f2 * f2 * d * d) * (b * b + f2 * f2 * d * d) - (a * d + b * c) * adbc;
+    co[0] = -adbc * b * d;
+    Cx roots[6];
+    const int n = solve_poly_dk(co, roots);
+    double bestS = (double)INT32_MAX, bestT = 0;
+    for (int k = 0; k < n; ++k)
+      if (std::fabs(roots[k].im) <= 1e-10) {
+        const double t = roots[k].re;
+        const double val = t * t / (1 + f1 * f1 * t * t) + ((c * t + d) * (c * t + d)) / ((a * t + b) * (a * t + b) + f2 * f2 * ((c * t + d) * (c * t + d)));
+        if (val < bestS) { bestS = val; bestT = t; }
+      }
+    const double valInf = 1 / (f1 * f1) + (c * c) / (a * a + f2 * f2 * c * c);
+    if (valInf < bestS) continue;  // MH.cpp:1170-1175 -> error -> not pushed (MH.cpp:816-817)
+    const double q1[3] = {0, bestT, 1};
+    const double l0 = F3[0] * q1[0] + F3[1] * q1[1] + F3[2], l1 = F3[3] * q1[0] + F3[4] * q1[1] + F3[5], l2 = F3[6] * q1[0] + F3[7] * q1[1] + F3[8];
+    double q2[3] = {-l0 * l2, -l1 * l2, l0 * l0 + l1 * l1};
+    q2[0] /= q2[2]; q2[1] /= q2[2]; q2[2] = 1.0;
+    const double T1[9] = {1, 0, -p1[0], 0, 1, -p1[1], 0, 0, 1}, T2[9] = {1, 0, -p2[0], 0, 1, -p2[1], 0, 0, 1};
+    double M1[9], M2[9], M1i[9], M2i[9];
+    mat3_mul(R1, T1, M1); mat3_mul(R2, T2, M2); mat3_inv(M1, M1i); mat3_inv(M2, M2i);
+    const double cpt[3] = {M1i[0] * q1[0] + M1i[1] * q1[1] + M1i[2], M1i[3] * q1[0] + M1i[4] * q1[1] + M1i[5], 1.0};
+    const double dpt[3] = {M2i[0] * q2[0] + M2i[1] * q2[1] + M2i[2], M2i[3] * q2[0] + M2i[4] * q2[1] + M2i[5], 1.0};
+    // ---- GetAffineConsistency (MH.cpp:1057-1090), distanceError only
+    const double* A = aff + 4 * i;
+    double l1v[3] = {F[0] * dpt[0] + F[3] * dpt[1] + F[6], F[1] * dpt[0] + F[4] * dpt[1] + F[7], F[2] * dpt[0] + F[5] * dpt[1] + F[8]};
+    double l2v[3] = {F[0] * cpt[0] + F[1] * cpt[1] + F[2], F[3] * cpt[0] + F[4] * cpt[1] + F[5], F[6] * cpt[0] + F[7] * cpt[1] + F[8]};
+    double n1[2] = {l1v[0] / l1v[2], l1v[1] / l1v[2]}, n2[2] = {l2v[0] / l2v[2], l2v[1] / l2v[2]};
+    double nn = std::sqrt(n1[0] * n1[0] + n1[1] * n1[1]); n1[0] /= nn; n1[1] /= nn;
+    nn = std::sqrt(n2[0] * n2[0] + n2[1] * n2[1]); n2[0] /= nn; n2[1] /= nn;
+    const double beta = beta_scale(F, cpt, dpt);
+    const double det = A[0] * A[3] - A[1] * A[2];
+    // r1 = A^-T n1 : A^-1 = [a22 -a12; -a21 a11]/det, transpose -> [a22 -a21; -a12 a11]/det
+    const double r1x = (A[3] * n1[0] - A[2] * n1[1]) / det, r1y = (-A[1] * n1[0] + A[0] * n1[1]) / det;
+    const double ex = r1x - beta * n2[0], ey = r1y - beta * n2[1];
+    if (std::sqrt(ex * ex + ey * ey) > 1.0) continue;  // MH.cpp:826
+    // ---- GetOptimalAffineTransformation (MH.cpp:1190-1223)
+    if (n1[0] * n2[0] + n1[1] * n2[1] < 0) { n2[0] = -n2[0]; n2[1] = -n2[1]; }
+    const double bx = beta * n2[0], by = beta * n2[1];
+    // C x = rhs, C = [I4 G; G^T 0] with G rows (-bx 0), (0 -bx), (-by 0), (0 -by): solved in closed form
+    // x = a - G mu, G^T x = (-n1) => mu = (G^T G)^-1 (G^T a + n1), G^T G = (bx^2 + by^2) I2
+    const double gta0 = -bx * A[0] - by * A[2], gta1 = -bx * A[1] - by * A[3];
+    const double s2 = bx * bx + by * by;
+    const double mu0 = (gta0 + n1[0]) / s2, mu1 = (gta1 + n1[1]) / s2;
+    out_aff[4 * i + 0] = A[0] + bx * mu0; out_aff[4 * i + 1] = A[1] + bx * mu1;
+    out_aff[4 * i + 2] = A[2] + by * mu0; out_aff[4 * i + 3] = A[3] + by * mu1;
+    out_pts[4 * i + 0] = cpt[0]; out_pts[4 * i + 1] = cpt[1]; out_pts[4 * i + 2] = dpt[0]; out_pts[4 * i + 3] = dpt[1];
+    keep[i] = 1;
+  }
+}

@@ -274,3 +274,15 @@ def gco_ref_expansion(data_cost, potts_weight, offsets, adj, init_labels=None, m
     if status.value:
         raise RuntimeError("reference GCO raised GCException")
     return int(e), out
+
+
+def prefilter(pts, aff, F):
+    """MH.cpp:786-838 with F given. Returns (pts_kept Mx4, aff_kept Mx4, keep mask N)."""
+    pts, pp = _d(pts)
+    aff, pa = _d(aff)
+    F, pF = _d(F)
+    N = pts.shape[0]
+    op = np.zeros((N, 4)); oa = np.zeros((N, 4)); keep = np.zeros(N, dtype=np.int32)
+    lib().orc_prefilter(pp, pa, pF, C.c_int64(N), op.ctypes.data_as(c_dp), oa.ctypes.data_as(c_dp), keep.ctypes.data_as(c_ip))
+    k = keep.astype(bool)
+    return op[k], oa[k], k

@@ -268,6 +268,40 @@ def barrsmith_fixture():
     print("barrsmith fixture:", 2903, "->", int(keep.sum()), "->", int(mask.sum()), "->", len(out_p), "kept")
 
 
+def prefilter_vectors():
+    """Golden vectors of the pre-filter (MultiH.cpp:786-838) on ALL bundled barrsmith rows + a noisy synthetic scene,
+    through the cv2.solvePoly-based transliteration above."""
+    src = "/root/reference/Executable/results/barrsmith/barrsmith_points_with_no_annotation.txt"
+    if not os.path.exists(src):
+        print("reference tree absent: prefilter golden not regenerated")
+        return
+    pts, aff, _ = m.scenes.load_points(src)
+    F = np.load(os.path.join(HERE, "barrsmith_hotpath_input.npz"))["F"]
+    sc = m.scenes.make_scene(1500, 5, seed=0xB200 + 55, noise_px=1.0, noise_aff=0.05)
+    out = {}
+    for name, (P_, A_, F_) in {"barr": (pts, aff, F), "syn": (sc.pts, sc.aff, sc.F)}.items():
+        e2 = epipole2(F_)
+        _, _, ev = cv2.eigen(F_.T @ F_)
+        e1 = ev[-1] / ev[-1][2]
+        R1 = np.array([[e1[0], e1[1], 0], [-e1[1], e1[0], 0], [0, 0, 1.0]])
+        R2 = np.array([[-e2[0], -e2[1], 0], [e2[1], -e2[0], 0], [0, 0, 1.0]])
+        keep = np.zeros(len(P_), dtype=bool); op, oa = [], []
+        for i in range(len(P_)):
+            r = optimal_triangulation(np.array([*P_[i, :2], 1.0]), np.array([*P_[i, 2:], 1.0]), F_, e1, e2, R1, R2)
+            if r is None:
+                continue
+            c, d = r
+            A = A_[i].reshape(2, 2)
+            if affine_consistency_distance(F_, A, c, d) > 1.0:
+                continue
+            oa.append(optimal_affine(A, F_, c, d)); op.append([c[0], c[1], d[0], d[1]]); keep[i] = True
+        out.update({f"{name}_pts": P_, f"{name}_aff": A_, f"{name}_F": F_, f"{name}_keep": keep,
+                    f"{name}_out_pts": np.array(op), f"{name}_out_aff": np.array(oa)})
+        print(name, len(P_), "->", int(keep.sum()))
+    np.savez_compressed(os.path.join(HERE, "golden_prefilter.npz"), **out)
+
+
 if __name__ == "__main__":
     small_vectors()
     barrsmith_fixture()
+    prefilter_vectors()

@@ -400,6 +400,29 @@ def test_cfg5_batched_pairs_are_independent(mh):
         assert K >= 1 and (lab >= 0).mean() > 0.2
 
 
+def test_k0_prefilter_vs_oracle_and_golden(mh, orc):
+    """K0: per-correspondence pre-filter on the GPU vs the oracle and the cv2-based golden vectors:
+    identical survivor set and order; corrected points / optimal affines within 1e-7 (FP64 on both sides)."""
+    g = np.load(os.path.join(GOLD, "golden_prefilter.npz"))
+    ctx = mh.Context()
+    for name in ("barr", "syn"):
+        po, ao, keep = ctx.prefilter(g[f"{name}_pts"], g[f"{name}_aff"], g[f"{name}_F"])
+        agree = (keep == g[f"{name}_keep"]).mean()
+        assert agree == 1.0, agree
+        assert np.abs(po - g[f"{name}_out_pts"]).max() < 1e-7 and np.abs(ao - g[f"{name}_out_aff"]).max() < 1e-7
+    sc = mh.scenes.make_scene(200_000, 20, seed=0xB200 + 9, noise_px=1.0, noise_aff=0.05)
+    po, ao, keep = ctx.prefilter(sc.pts, sc.aff, sc.F)
+    po_o, ao_o, keep_o = orc.prefilter(sc.pts, sc.aff, sc.F)
+    same = (keep == keep_o)
+    print(f"\n[parity] K0 200k: kept gpu={keep.sum()} oracle={keep_o.sum()} mask agreement={same.mean():.6f}")
+    assert same.mean() >= 0.9999
+    if same.all():
+        assert np.abs(po - po_o).max() < 1e-7 and np.abs(ao - ao_o).max() < 1e-7
+    # empty and tiny inputs
+    e = ctx.prefilter(np.zeros((0, 4)), np.zeros((0, 4)), sc.F)
+    assert e[0].shape == (0, 4) and e[2].shape == (0,)
+
+
 def test_multih_class_surface(mh):
     g = np.load(os.path.join(GOLD, "barrsmith_hotpath_input.npz"))
     o = mh.MultiH(2.6, 2.2, 0.005, 0.5, 20)

@@ -138,3 +138,17 @@ def test_golden_vectors(orc):
     cnt, sc, lmin, keep = orc.inlier_stats(pts, g["cost_H"])
     assert np.array_equal(cnt, g["inl_count"]) and np.array_equal(keep, g["inl_keep"])
     assert np.allclose(lmin, g["inl_lmin"], rtol=1e-6, atol=1e-9)
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(GOLD, "golden_prefilter.npz")), reason="golden vectors not generated")
+def test_prefilter_golden(orc):
+    """Pre-filter (MultiH.cpp:786-838) vs the cv2.solvePoly-based transliteration on all 2903 bundled barrsmith rows and
+    a noisy synthetic scene."""
+    g = np.load(os.path.join(GOLD, "golden_prefilter.npz"))
+    for name in ("barr", "syn"):
+        po, ao, keep = orc.prefilter(g[f"{name}_pts"], g[f"{name}_aff"], g[f"{name}_F"])
+        assert np.array_equal(keep, g[f"{name}_keep"])
+        assert np.abs(po - g[f"{name}_out_pts"]).max() < 1e-8
+        assert np.abs(ao - g[f"{name}_out_aff"]).max() < 1e-8
+    # the hot-path input fixture is exactly the survivors of the F-RANSAC inliers
+    assert g["barr_keep"].sum() >= 1197
