@@ -65,6 +65,9 @@ typedef struct mh_params {
                              other sites inside the radius; <= 0 = the full radius ball                      */
   int32_t precise_pipeline; /* mh_process data path: 1 (default) = FP64 pixel-space kernels tracking the reference's
                                arithmetic; 0 = FP32 normalised throughput kernels (same control flow)        */
+  int32_t prefilter;        /* mh_process: 1 = run K0 first (MultiH.cpp:807-838: Hartley-Sturm correction, affine
+                               consistency test, optimal affine) as Process() does after estimating F; dropped
+                               correspondences get label -2.  0 (default) = inputs are already refined             */
 } mh_params;
 
 void mh_default_params(mh_params* p); /* main.cpp:55-59: 2.6 / 2.2 / 0.005 / 0.5 / 20 */
@@ -201,7 +204,7 @@ mh_status mh_alpha_expansion(mh_ctx* ctx, const int32_t* cost_host, int32_t N, i
  * MultiH::Process (MultiH.cpp:42-98) from ComputeLocalHomographies on, with F supplied:
  * K1 -> 10-D mean-shift -> cluster 3PT -> { merge (6-D mean-shift, inlier/straightness test) <-> label (K2 dense costs
  * -> host alpha-expansion) + refit (K4) } until convergence (MultiH.cpp:224-312).
- * labels_out: N, -1 = outlier (GetLabels, MultiH.h:62); H_out: up to Kmax x 9 px (GetHomography, MultiH.h:69);
+ * labels_out: N, -1 = outlier (GetLabels, MultiH.h:62), -2 = dropped by the pre-filter (params.prefilter only); H_out: up to Kmax x 9 px (GetHomography, MultiH.h:69);
  * K_out = GetClusterNumber (MultiH.h:67). */
 mh_status mh_process(mh_ctx* ctx, const double* pts_host, const double* aff_host, const double F[9], int32_t N,
                      int32_t* labels_out, double* H_out, int32_t Kmax, int32_t* K_out);

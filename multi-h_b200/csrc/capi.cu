@@ -152,6 +152,7 @@ void mh_default_params(mh_params* p) {
   p->max_gc_cycles = 1000;   // MultiH.cpp:543
   p->max_neighbours = 31;    // FLANN default SearchParams: checks = 32 (query included)
   p->precise_pipeline = 1;
+  p->prefilter = 0;
 }
 
 mh_status mh_create(const mh_params* params, int device, mh_ctx** out) {

@@ -30,12 +30,18 @@ using namespace mh;
 
 namespace {
 
-struct DevBuf {
+struct DevBuf {  // grow-only device buffer: the alternating loop re-uses its buffers instead of cudaMalloc/cudaFree per step
   void* p = nullptr;
+  uint64_t cap = 0;
   ~DevBuf() { if (p) cudaFree(p); }
   mh_status alloc(mh_ctx* ctx, uint64_t bytes) {
-    if (p) { cudaFree(p); p = nullptr; }
-    return check_cuda(ctx, cudaMalloc(&p, std::max<uint64_t>(bytes, 256)), "cudaMalloc");
+    bytes = std::max<uint64_t>(bytes, 256);
+    if (p && cap >= bytes) return MH_OK;
+    if (p) { cudaStreamSynchronize(ctx->stream); cudaFree(p); p = nullptr; cap = 0; }
+    const uint64_t want = bytes + bytes / 4;
+    mh_status st = check_cuda(ctx, cudaMalloc(&p, want), "cudaMalloc");
+    if (st == MH_OK) cap = want;
+    return st;
   }
   template <typename T> T* as() { return (T*)p; }
 };
@@ -81,14 +87,43 @@ mh_status mh_process(mh_ctx* ctx, const double* pts, const double* aff, const do
   ctx->rng_state = P.rng_seed;  // every Process() call starts from the same generator state, like a fresh run of the reference
   MH_TRY(mh_set_geometry(ctx, F, nullptr, nullptr, pts, N));
 
-  DevBuf b_pts, b_aff, b_pts64, b_aff64, b_hyp_pt, b_hyp_pt64, b_feat, b_centres, b_assign, b_hyp, b_hyp64, b_keep, b_cost,
-      b_labels, b_modes_hyp, b_modes_hyp64, b_feat6, b_scatter;
+  DevBuf b_pts, b_aff, b_pts64, b_aff64, b_raw_p, b_raw_a, b_keepmask, b_hyp_pt, b_hyp_pt64, b_feat, b_centres, b_assign, b_hyp,
+      b_hyp64, b_keep, b_cost, b_labels, b_modes_hyp, b_modes_hyp64, b_feat6, b_scatter;
+  const int32_t N_in = N;
+  std::vector<int32_t> keepmask;      // prefilter survivors (only with params.prefilter)
+  std::vector<double> kept_pts_host;  // their refined coordinates, for the host neighbourhood search
+  if (P.prefilter) {
+    // ---- per-correspondence refinement of GetFundamentalMatrixAndRefineData (MultiH.cpp:807-838), K0 ------------
+    MH_TRY(b_raw_p.alloc(ctx, sizeof(double) * 4 * (uint64_t)N));
+    MH_TRY(b_raw_a.alloc(ctx, sizeof(double) * 4 * (uint64_t)N));
+    MH_TRY(b_pts64.alloc(ctx, sizeof(double) * 4 * (uint64_t)N));
+    MH_TRY(b_aff64.alloc(ctx, sizeof(double) * 4 * (uint64_t)N));
+    MH_TRY(b_keepmask.alloc(ctx, sizeof(int32_t) * (uint64_t)N));
+    MH_CUDA(ctx, cudaMemcpyAsync(b_raw_p.p, pts, sizeof(double) * 4 * (size_t)N, cudaMemcpyHostToDevice, ctx->stream));
+    MH_CUDA(ctx, cudaMemcpyAsync(b_raw_a.p, aff, sizeof(double) * 4 * (size_t)N, cudaMemcpyHostToDevice, ctx->stream));
+    int64_t M = 0;
+    MH_TRY(launch_prefilter(ctx, b_raw_p.as<double>(), b_raw_a.as<double>(), F, N, b_pts64.as<double>(), b_aff64.as<double>(),
+                            b_keepmask.as<int32_t>(), &M));
+    keepmask.resize(N);
+    MH_TRY(mh_memcpy_d2h(ctx, keepmask.data(), b_keepmask.p, sizeof(int32_t) * (size_t)N));
+    if (trace) std::fprintf(stderr, "[Multi-H] %lld points kept from the initial %d after filtering.\n", (long long)M, N);  // MultiH.cpp:840
+    if (M < 8) {  // MultiH.cpp:842-847: degenerate, not enough points remained
+      for (int i = 0; i < N_in; ++i) labels_out[i] = keepmask[i] ? -1 : -2;
+      return fail(ctx, MH_EDEGENERATE, "Degenerate case, not enough points remained (MultiH.cpp:842-847)");
+    }
+    N = (int32_t)M;
+    kept_pts_host.resize(4 * (size_t)N);
+    MH_TRY(mh_memcpy_d2h(ctx, kept_pts_host.data(), b_pts64.p, sizeof(double) * 4 * (size_t)N));
+    pts = kept_pts_host.data();
+    MH_TRY(mh_set_geometry(ctx, F, nullptr, nullptr, pts, N));  // normalisation from the refined set
+  } else {
+    MH_TRY(b_pts64.alloc(ctx, sizeof(double) * 4 * (uint64_t)N));
+    MH_TRY(b_aff64.alloc(ctx, sizeof(double) * 4 * (uint64_t)N));
+    MH_CUDA(ctx, cudaMemcpyAsync(b_pts64.p, pts, sizeof(double) * 4 * (size_t)N, cudaMemcpyHostToDevice, ctx->stream));
+    MH_CUDA(ctx, cudaMemcpyAsync(b_aff64.p, aff, sizeof(double) * 4 * (size_t)N, cudaMemcpyHostToDevice, ctx->stream));
+  }
   MH_TRY(b_pts.alloc(ctx, sizeof(float4) * (uint64_t)N));
   MH_TRY(b_aff.alloc(ctx, sizeof(float4) * (uint64_t)N));
-  MH_TRY(b_pts64.alloc(ctx, sizeof(double) * 4 * (uint64_t)N));
-  MH_TRY(b_aff64.alloc(ctx, sizeof(double) * 4 * (uint64_t)N));
-  MH_CUDA(ctx, cudaMemcpyAsync(b_pts64.p, pts, sizeof(double) * 4 * (size_t)N, cudaMemcpyHostToDevice, ctx->stream));
-  MH_CUDA(ctx, cudaMemcpyAsync(b_aff64.p, aff, sizeof(double) * 4 * (size_t)N, cudaMemcpyHostToDevice, ctx->stream));
   MH_TRY(launch_normalize_points(ctx, b_pts64.as<double>(), b_aff64.as<double>(), N, b_pts.as<float4>(), b_aff.as<float4>()));
   const double* pts64 = precise ? b_pts64.as<double>() : nullptr;
   const double* aff64 = precise ? b_aff64.as<double>() : nullptr;
@@ -261,7 +296,12 @@ mh_status mh_process(mh_ctx* ctx, const double* pts, const double* aff, const do
   ctx->iterations = iteration_number - 1;  // MultiH.cpp:311
   ctx->stage_ms[3] = now_ms() - t0;
 
-  std::memcpy(labels_out, labeling.data(), sizeof(int32_t) * (size_t)N);
+  if (P.prefilter) {  // labels of the survivors in input order; -2 marks correspondences the pre-filter dropped
+    int j = 0;
+    for (int i = 0; i < N_in; ++i) labels_out[i] = keepmask[i] ? labeling[j++] : -2;
+  } else {
+    std::memcpy(labels_out, labeling.data(), sizeof(int32_t) * (size_t)N);
+  }
   *K_out = K;
   if (H_out)
     for (int k = 0; k < std::min(K, (int)Kmax); ++k) {

@@ -16,7 +16,9 @@ def _csr(assign, C):
 
 
 def oracle_process(pts, aff, F, thr=2.2, locality=0.005, lam=0.5, straightness=0.005, max_iterations=500,
-                   convergence=1e-5, max_gc_cycles=1000, rng_state=1, max_neighbours=31, use_ref_gco=True, expansion=None, trace=None):
+                   convergence=1e-5, max_gc_cycles=1000, rng_state=1, max_neighbours=31, prefilter=False, use_ref_gco=True, expansion=None, trace=None):
+    if prefilter:                                                            # MultiH.cpp:807-838
+        pts, aff, keepmask = orc.prefilter(pts, aff, F)
     N = len(pts)
     e2 = orc.epipole2(F)
     H_pt = orc.haf_hypotheses(pts, aff, F, e2)                              # MultiH.cpp:696-717
@@ -64,4 +66,8 @@ def oracle_process(pts, aff, F, thr=2.2, locality=0.005, lam=0.5, straightness=0
             energy_final = energy
             break
         last_energy = energy
+    if prefilter:
+        full = np.full(len(keepmask), -2, dtype=np.int32)
+        full[keepmask] = labeling
+        labeling = full
     return labeling, hyp, dict(iterations=it - 1, energy=energy_final)  # final_iteration_number, MultiH.cpp:311

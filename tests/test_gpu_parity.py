@@ -423,6 +423,27 @@ def test_k0_prefilter_vs_oracle_and_golden(mh, orc):
     assert e[0].shape == (0, 4) and e[2].shape == (0,)
 
 
+def test_pipeline_from_raw_correspondences(mh, orc):
+    """Process() as the reference runs it after estimating F: pre-filter (K0) + hot path, on the RAW bundled barrsmith
+    rows that pass the F-RANSAC (golden fixture), vs the oracle pipeline with the same switch."""
+    from ref_pipeline import oracle_process
+
+    g = np.load(os.path.join(GOLD, "golden_prefilter.npz"))
+    F = g["barr_F"]
+    x1 = np.c_[g["barr_pts"][:, :2], np.ones(len(g["barr_pts"]))]; x2 = np.c_[g["barr_pts"][:, 2:], np.ones(len(x1))]
+    l = x1 @ F.T                                           # epipolar lines in image 2
+    dist = np.abs(np.einsum("ij,ij->i", x2, l)) / np.hypot(l[:, 0], l[:, 1])
+    inl = dist < 2.6                                       # stands in for the RANSAC mask of MultiH.cpp:775
+    pts, aff = g["barr_pts"][inl], g["barr_aff"][inl]
+    ctx = mh.Context(mh.capi.default_params(prefilter=1))
+    lab, H, K = ctx.process(pts, aff, F)
+    lab_o, H_o, info = oracle_process(pts, aff, F, prefilter=True)
+    agree = (lab == lab_o).mean()
+    print(f"\n[parity] raw barrsmith N={len(pts)} kept={int((lab > -2).sum())}: K gpu={K} oracle={len(H_o)} agreement={agree:.4f}")
+    assert np.array_equal(lab == -2, lab_o == -2)
+    assert K == len(H_o) and agree >= 0.99
+
+
 def test_multih_class_surface(mh):
     g = np.load(os.path.join(GOLD, "barrsmith_hotpath_input.npz"))
     o = mh.MultiH(2.6, 2.2, 0.005, 0.5, 20)
