@@ -217,6 +217,8 @@ mh_status mh_get_stage_ms(const mh_ctx* ctx, double ms[5]);
 /* ---- diagnostics (measurement aids, not part of the reference surface) -------- */
 /* FP32 FMA-pipe peak of this GPU: variant 0 = scalar FFMA, 1 = packed FFMA2; the roofline denominator of K2. */
 mh_status mh_diag_fp32_peak(mh_ctx* ctx, int32_t variant, int32_t iters, double* tflops_out, double* ms_out);
+/* legacy tensor path probe: mma.sync.m16n8k8 TF32 dense TFLOP/s and warp-MMAs per clock per SM (at 1965 MHz) */
+mh_status mh_diag_mma_tf32_peak(mh_ctx* ctx, int32_t iters, double* tflops_out, double* mma_per_clk_per_sm);
 /* K2 fused inner loop: 1 = packed FFMA2 (default), 0 = scalar FFMA (A/B evidence only). */
 mh_status mh_diag_set_fused_variant(mh_ctx* ctx, int32_t variant);
 /* K2 fast path launch shape (threads/CTA x CTAs/SM): 0 = 256x3, 1 = 256x2, 2 = 256x4, 3 = 128x5, 4 = 128x6,
