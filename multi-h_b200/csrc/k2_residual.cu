@@ -647,6 +647,209 @@ cost_argmin_t_kernel(const float4* __restrict__ pts, long long N, const u64* __r
   }
 }
 
+// ----------------------------------------------------------------------------
+// v5: the 3x3 homography product on the tensor cores.  60 % of the FP32 work of a residual is the projective product
+// (s, xn, yn) = H (x, y, 1)^T — a GEMM with inner dimension 3.  Here it runs as mma.sync.m16n8k8 TF32 with the 3xTF32
+// split packed INTO the k = 8 inner dimension, so one MMA gives FP32-grade sums:
+//     A[point][k]   = [ xhi, yhi, 1, xlo, xhi, yhi, ylo, 1 ]                (16 correspondences x 8)
+//     B_s[k][hyp]   = [ h6hi, h7hi, h8hi, h6hi, h6lo, h7lo, h7hi, h8lo ]    (8 x 8 hypotheses; same pattern for xn, yn)
+//     s = xhi h6hi + yhi h7hi + h8hi + xlo h6hi + xhi h6lo + yhi h7lo + ylo h7hi + h8lo     (only lo*lo terms dropped)
+// Each thread then owns 2 correspondences (fragment rows g, g+8) x 2 hypotheses (columns 2t, 2t+1) per MMA triple and
+// finishes them on the FP32 pipe with 4 FFMA2 + 1 FADD2 per pair (reciprocal, residual, folded interval / inlier tests
+// exactly as in v3).  The tensor-core sums only feed the conservative argmin filter and the inlier counts; every
+// candidate is re-evaluated with the dense kernel's FP32 instruction sequence, so (cost, label) stay bit-identical.
+// Per-correspondence argmin state is replicated in the 4 lanes of a quad and kept coherent by a quad min-reduce in the
+// (rare) update path; per-hypothesis inlier bits are funnel-shifted into masks and added to shared counters once per
+// 8-hypothesis block.
+// ----------------------------------------------------------------------------
+__device__ __forceinline__ unsigned to_tf32(float x) {
+  unsigned r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const unsigned (&a)[4], unsigned b0, unsigned b1) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%10,%10,%10};"
+               : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1), "f"(0.f));
+}
+
+constexpr int MMA_THREADS = 256;
+constexpr int MMA_CH = 512;  // hypotheses staged per chunk (48 KB of split fragments)
+
+template <bool COUNT_INLIERS, int MINB, int PB>
+__global__ void __launch_bounds__(MMA_THREADS, MINB)
+cost_argmin_mma_kernel(const float4* __restrict__ pts, long long N, const float* __restrict__ hyp, int K, int k_per_block,
+                       CostParams cp, FastOut o, int use_atomic_best) {
+  // dynamic shared memory (56 KB > the 48 KB static limit):
+  //   sB   [MMA_CH][3][4] float2 : [hyp][s|xn|yn][t] = {B[t][hyp], B[t+4][hyp]} as tf32 bit patterns
+  //   sCntW[warps][MMA_CH] u16   : per-warp inlier counts of the chunk (<= 16 PB each)
+  extern __shared__ __align__(16) unsigned char mma_smem[];
+  float2 (*sB)[3][4] = reinterpret_cast<float2 (*)[3][4]>(mma_smem);
+  unsigned short (*sCntW)[MMA_CH] = reinterpret_cast<unsigned short (*)[MMA_CH]>(mma_smem + sizeof(float2) * MMA_CH * 12);
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+  constexpr int PTS_PER_WARP = 16 * PB, TILE = (MMA_THREADS / 32) * PTS_PER_WARP;
+  const long long tile0 = (long long)blockIdx.x * TILE + (long long)warp * PTS_PER_WARP;
+  const int kbeg = blockIdx.y * k_per_block;
+  const int kend = min(K, kbeg + k_per_block);
+
+  // ---- per-thread correspondence state: rows g and g+8 of each of the warp's PB 16-row blocks ----------------------
+  unsigned A[PB][4];
+  float X[PB][2], Y[PB][2], NX2[PB][2], NY2[PB][2], NEGMID[PB][2], HALF[PB][2], C[PB][2];
+  unsigned BEST[PB][2];
+  const unsigned best_init = ((unsigned)min(cp.cost_outlier, 0xffff) << 16);
+#pragma unroll
+  for (int pb = 0; pb < PB; ++pb)
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const long long idx = tile0 + pb * 16 + g + 8 * r;
+      const float4 q = pts[idx < N ? idx : N - 1];
+      X[pb][r] = q.x; Y[pb][r] = q.y; NX2[pb][r] = -q.z; NY2[pb][r] = -q.w;
+      BEST[pb][r] = best_init;
+      fast_thresholds(cp.cost_outlier, cp, NEGMID[pb][r], HALF[pb][r]);
+      C[pb][r] = -NEGMID[pb][r] - cp.thr2;
+      if (idx >= N) { HALF[pb][r] = -1.f; C[pb][r] = 3.0e38f; }
+      // A fragment entries of this row: k = t and k = t + 4 of [xhi, yhi, 1, xlo, xhi, yhi, ylo, 1]
+      const unsigned xhi = to_tf32(q.x), yhi = to_tf32(q.y);
+      const unsigned xlo = to_tf32(q.x - __uint_as_float(xhi)), ylo = to_tf32(q.y - __uint_as_float(yhi));
+      const unsigned one = 0x3f800000u;
+      A[pb][r] = t == 0 ? xhi : t == 1 ? yhi : t == 2 ? one : xlo;      // a0 (row g) / a1 (row g+8): k = t
+      A[pb][2 + r] = t == 0 ? xhi : t == 1 ? yhi : t == 2 ? ylo : one;  // a2 / a3: k = t + 4
+    }
+  const u64 ONE2 = pk(1.f, 1.f);
+
+  for (int c0 = kbeg; c0 < kend; c0 += MMA_CH) {
+    // ---- stage a chunk of hypotheses as 3xTF32 split B fragments ---------------------------------------------------------
+    __syncthreads();
+    for (int j = threadIdx.x; j < MMA_CH; j += MMA_THREADS) {
+      const int ih = c0 + j;
+      float h[9];
+      if (ih < kend) {
+        const float4* p = reinterpret_cast<const float4*>(hyp + (size_t)ih * 12);
+        const float4 u = p[0], v = p[1], w = p[2];
+        h[0] = u.x; h[1] = u.y; h[2] = u.z; h[3] = u.w; h[4] = v.x; h[5] = v.y; h[6] = v.z; h[7] = v.w; h[8] = w.x;
+      } else {
+        h[0] = h[1] = h[3] = h[4] = h[6] = h[7] = 0.f; h[2] = h[5] = 1e18f; h[8] = 1.f;
+      }
+#pragma unroll
+      for (int m = 0; m < 3; ++m) {
+        const int base = m == 0 ? 6 : m == 1 ? 0 : 3;  // s uses (h6,h7,h8); xn (h0,h1,h2); yn (h3,h4,h5)
+        const float ha = h[base], hb = h[base + 1], hc = h[base + 2];
+        const float ahi = __uint_as_float(to_tf32(ha)), bhi = __uint_as_float(to_tf32(hb)), chi = __uint_as_float(to_tf32(hc));
+        const float alo = __uint_as_float(to_tf32(ha - ahi)), blo = __uint_as_float(to_tf32(hb - bhi)),
+                    clo = __uint_as_float(to_tf32(hc - chi));
+        // B[k] = [ahi, bhi, chi, ahi, alo, blo, bhi, clo]; entry [t] = {B[t], B[t+4]}
+        float4* d = reinterpret_cast<float4*>(&sB[j][m][0]);
+        d[0] = make_float4(ahi, alo, bhi, blo);
+        d[1] = make_float4(chi, bhi, ahi, clo);
+      }
+    }
+    __syncthreads();
+    const int nblk = (min(MMA_CH, kend - c0) + 7) >> 3;
+    const float2* bp = &sB[g][0][t];                      // + hb * 8 hypotheses = hb * 96 float2
+    unsigned short* cw = &sCntW[warp][2 * t];
+
+#pragma unroll 1
+    for (int hb = 0; hb < nblk; hb += 2) {                // two 8-hypothesis blocks per trip
+      unsigned packed = 0u;                               // byte fields: inlier counts of (blk A: 2t, 2t+1), (blk B: 2t, 2t+1)
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        const float2 bs = bp[(hb + hh) * 96], bx = bp[(hb + hh) * 96 + 4], by = bp[(hb + hh) * 96 + 8];
+        unsigned mask0 = 0u, mask1 = 0u;
+        float T_[PB][2][2];
+        bool cand = false;
+#pragma unroll
+        for (int pb = 0; pb < PB; ++pb) {
+          float S[4], XN[4], YN[4];
+          mma_tf32(S, A[pb], __float_as_uint(bs.x), __float_as_uint(bs.y));
+          mma_tf32(XN, A[pb], __float_as_uint(bx.x), __float_as_uint(bx.y));
+          mma_tf32(YN, A[pb], __float_as_uint(by.x), __float_as_uint(by.y));
+#pragma unroll
+          for (int r = 0; r < 2; ++r) {
+            const u64 rr = pk(rcp_approx(S[2 * r]), rcp_approx(S[2 * r + 1]));
+            const u64 dx = fma2(pk(XN[2 * r], XN[2 * r + 1]), rr, pk(NX2[pb][r], NX2[pb][r]));
+            const u64 dy = fma2(pk(YN[2 * r], YN[2 * r + 1]), rr, pk(NY2[pb][r], NY2[pb][r]));
+            const u64 tt = fma2(dx, dx, fma2(dy, dy, pk(NEGMID[pb][r], NEGMID[pb][r])));  // d2 - mid
+            upk(tt, T_[pb][r][0], T_[pb][r][1]);
+            if (COUNT_INLIERS) {
+              float va, vb;
+              upk(fma2(tt, ONE2, pk(C[pb][r], C[pb][r])), va, vb);  // d2 - thr2: sign bit = inlier
+              mask0 = __funnelshift_l(__float_as_uint(va), mask0, 1);
+              mask1 = __funnelshift_l(__float_as_uint(vb), mask1, 1);
+            }
+            cand = cand || (fminf(fabsf(T_[pb][r][0]), fabsf(T_[pb][r][1])) < HALF[pb][r]);
+          }
+        }
+        if (COUNT_INLIERS) packed |= (__popc(mask0) | (__popc(mask1) << 8)) << (16 * hh);
+        if (__any_sync(0xffffffffu, cand)) {  // warp-uniform: some lane holds a candidate in this 8-block -> exact update
+#pragma unroll
+          for (int pb = 0; pb < PB; ++pb)
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+              unsigned mine = 0xffffffffu;
+#pragma unroll
+              for (int e = 0; e < 2; ++e) {
+                if (fabsf(T_[pb][r][e]) < HALF[pb][r]) {
+                  const int ih = c0 + (hb + hh) * 8 + 2 * t + e;  // 0-based hypothesis index
+                  if (ih < kend) {
+                    const float4* hp = reinterpret_cast<const float4*>(hyp + (size_t)ih * 12);
+                    const float4 u = hp[0], v = hp[1], w = hp[2];
+                    const float hx[9] = {u.x, u.y, u.z, u.w, v.x, v.y, v.z, v.w, w.x};
+                    const float d2 = residual(hx, X[pb][r], Y[pb][r], -NX2[pb][r], -NY2[pb][r]);
+                    if (d2 < cp.T) mine = min(mine, ((unsigned)cost_in_range(d2, cp) << 16) | (unsigned)(ih + 1));
+                  }
+                }
+              }
+              mine = min(mine, __shfl_xor_sync(0xffffffffu, mine, 1));  // the 4 lanes of a quad share rows g, g+8
+              mine = min(mine, __shfl_xor_sync(0xffffffffu, mine, 2));
+              if (mine < BEST[pb][r]) {
+                BEST[pb][r] = mine;
+                // labels rise along the loop for a given correspondence: only strictly cheaper candidates matter
+                fast_thresholds((int)(mine >> 16), cp, NEGMID[pb][r], HALF[pb][r]);
+                C[pb][r] = -NEGMID[pb][r] - cp.thr2;
+              }
+            }
+        }
+      }
+      if (COUNT_INLIERS) {
+        // sum the byte fields over the 8 lanes that share t (<= 2 PB per lane, <= 16 PB per field): 3 shuffles, then
+        // lanes g == 0 store this warp's counts of the two blocks (each (warp, hypothesis) is visited once per chunk)
+        packed += __shfl_xor_sync(0xffffffffu, packed, 4);
+        packed += __shfl_xor_sync(0xffffffffu, packed, 8);
+        packed += __shfl_xor_sync(0xffffffffu, packed, 16);
+        if (g == 0) {
+          *reinterpret_cast<unsigned*>(cw + hb * 8) = (packed & 0xffu) | ((packed & 0xff00u) << 8);
+          *reinterpret_cast<unsigned*>(cw + hb * 8 + 8) = ((packed >> 16) & 0xffu) | ((packed >> 8) & 0xff0000u);
+        }
+      }
+    }
+    if (COUNT_INLIERS) {
+      __syncthreads();
+      const int nh = min(MMA_CH, kend - c0);
+      for (int j = threadIdx.x; j < nh; j += MMA_THREADS) {
+        int v = 0;
+#pragma unroll
+        for (int w = 0; w < MMA_THREADS / 32; ++w) v += sCntW[w][j];
+        if (v) atomicAdd(o.inlier_count + c0 + j, v);
+      }
+    }
+  }
+  if (o.best && t == 0) {  // the quad holds identical state: lane t == 0 writes
+#pragma unroll
+    for (int pb = 0; pb < PB; ++pb)
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const long long idx = tile0 + pb * 16 + g + 8 * r;
+        const unsigned b = BEST[pb][r];
+        if (idx < N && (b & 0xffffu) != 0u) {
+          const u64 v = ((u64)(b >> 16) << 32) | (u64)(b & 0xffffu);
+          if (use_atomic_best) atomicMin(o.best + idx, v);
+          else o.best[idx] = v;
+        }
+      }
+  }
+}
+
 __global__ void fused_init_kernel(long long N, int K, int32_t* list_count, u64* best, int32_t* inlier_count,
                                   u64 best_init) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -720,7 +923,33 @@ mh_status launch_cost_fused(mh_ctx* ctx, const float4* d_pts, int64_t N, const f
       return MH_OK;
     };
     if (K >= 65535 || cp.cost_outlier > 0xffff) g_fast_config = std::min(g_fast_config, 6);  // v4 packs (cost, label) in 32 bits
+    auto launch_m = [&](auto kernel_cnt, auto kernel_nocnt, int pb) -> mh_status {
+      const int tile = (MMA_THREADS / 32) * 16 * pb;
+      const unsigned tiles_f = (unsigned)((N + tile - 1) / tile);
+      int ks = 1;
+      if ((int)tiles_f < want) ks = std::min((K + MMA_CH - 1) / MMA_CH, (want + (int)tiles_f - 1) / (int)tiles_f);
+      ks = std::max(1, ks);
+      int kpb = (K + ks - 1) / ks;
+      kpb = ((kpb + MMA_CH - 1) / MMA_CH) * MMA_CH;
+      ks = (K + kpb - 1) / kpb;
+      dim3 gridf(tiles_f, (unsigned)ks);
+      const size_t smem = sizeof(float2) * MMA_CH * 12 + sizeof(unsigned short) * (MMA_THREADS / 32) * MMA_CH;
+      if (cnt) {
+        MH_CUDA(ctx, cudaFuncSetAttribute(kernel_cnt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kernel_cnt<<<gridf, MMA_THREADS, smem, ctx->stream>>>(d_pts, N, d_hyp, K, kpb, cp, fo, ks > 1);
+      } else {
+        MH_CUDA(ctx, cudaFuncSetAttribute(kernel_nocnt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kernel_nocnt<<<gridf, MMA_THREADS, smem, ctx->stream>>>(d_pts, N, d_hyp, K, kpb, cp, fo, ks > 1);
+      }
+      return MH_OK;
+    };
     switch (g_fast_config) {
+      case 20: MH_TRY(launch_m(cost_argmin_mma_kernel<true, 2, 2>, cost_argmin_mma_kernel<false, 2, 2>, 2)); break;
+      case 21: MH_TRY(launch_m(cost_argmin_mma_kernel<true, 3, 2>, cost_argmin_mma_kernel<false, 3, 2>, 2)); break;
+      case 22: MH_TRY(launch_m(cost_argmin_mma_kernel<true, 2, 4>, cost_argmin_mma_kernel<false, 2, 4>, 4)); break;
+      case 23: MH_TRY(launch_m(cost_argmin_mma_kernel<true, 3, 1>, cost_argmin_mma_kernel<false, 3, 1>, 1)); break;
+      case 24: MH_TRY(launch_m(cost_argmin_mma_kernel<true, 4, 1>, cost_argmin_mma_kernel<false, 4, 1>, 1)); break;
+      case 25: MH_TRY(launch_m(cost_argmin_mma_kernel<true, 3, 3>, cost_argmin_mma_kernel<false, 3, 3>, 3)); break;
       case 10: launch_t(cost_argmin_t_kernel<true, 128, 6, 2, 512>, cost_argmin_t_kernel<false, 128, 6, 2, 512>, 128, 512, 512); break;
       case 11: launch_t(cost_argmin_t_kernel<true, 128, 5, 2, 512>, cost_argmin_t_kernel<false, 128, 5, 2, 512>, 128, 512, 512); break;
       case 12: launch_t(cost_argmin_t_kernel<true, 128, 4, 4, 512>, cost_argmin_t_kernel<false, 128, 4, 4, 512>, 128, 1024, 512); break;
