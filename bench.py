@@ -32,6 +32,9 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+METRIC = "correspondence x hypothesis residual evaluations per second (whole job)"
+WORKLOAD = ("cfg4: synthetic 200-plane scene, 4M affine correspondences x 8192 hypotheses "
+            "(200 planes + 7992 HAF hypotheses), correspondence-sharded")
 N_TOTAL = 4 * (1 << 20)
 N_PLANES = 200
 K_HYP = 8192
@@ -109,12 +112,12 @@ def run_reference(args):
     dt = time.perf_counter() - t0
     value = n_sample * K_HYP * args.steps / dt
     line = {
-        "impl": "reference", "metric": "correspondence x hypothesis residual evaluations per second", "value": value,
+        "impl": "reference", "metric": METRIC, "value": value,
         "unit": "residuals/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "cfg4: synthetic 200-plane scene, 4M correspondences x 8192 hypotheses "
-                               "(bounded sample per step)", "hypotheses": K_HYP},
+        "config": {"workload": WORKLOAD, "correspondences": N_TOTAL, "hypotheses": K_HYP,
+                   "step": f"bounded sample: {n_sample} correspondences x {K_HYP} hypotheses per step"},
         "cpu_baseline": {"value": value, "unit": "residuals/s", "cores": cores, "kind": "port",
                          "sample": f"{n_sample} correspondences x {K_HYP} hypotheses per step (dataEnergy + argmin + "
                                    f"inlier count, FP64 oracle port, {cores} threads)"},
@@ -360,12 +363,11 @@ def main():
                 "outlier_fraction": float((lab < 0).mean()), "iterations": pctx.iterations, "stage_ms": pctx.stage_ms()}
 
     line = {
-        "metric": "correspondence x hypothesis residual evaluations per second (whole job)",
+        "metric": METRIC,
         "value": value, "unit": "residuals/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "cfg4: synthetic 200-plane scene, 4M affine correspondences x 8192 hypotheses "
-                               "(200 planes + 7992 HAF hypotheses), correspondence-sharded",
+        "config": {"workload": WORKLOAD,
                    "correspondences": n_total, "hypotheses": K_HYP, "per_rank": n_loc,
                    "step": "K1 HAF + K2 fused cost/argmin/inlier-count + K4 refit (+ NCCL bcast/all-reduce for N>1)",
                    "l2": "256 MiB memset between steps, inside the timed region"},
