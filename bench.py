@@ -183,21 +183,42 @@ def main():
     k2_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
              for _ in range(args.steps + args.warmup + 1)]
 
+    # Multi-GPU: the statistics all-reduce of step i runs on NCCL's stream while step i+1 computes (double-buffered
+    # statistics); its solve is issued when the reduction has landed.  Everything of every step completes inside the
+    # timed region (finish_pending() before the closing event).
+    acc2 = [acc, torch.empty_like(acc)]
+    inl_total = torch.empty_like(fused["inliers"])  # whole-scene inlier counts (after the all-reduce)
+    state = {"cur": 0, "pending": None}
+
+    def finish_pending():
+        pend = state["pending"]
+        if pend is not None:
+            handle, b = pend
+            handle.wait()
+            ctx.pack_inlier_counts(inl_total, acc2[b], unpack=True)
+            ctx.refit_haf_solve(acc2[b], d_ref)                                              # K4 solves
+            state["pending"] = None
+
     def stats_and_refit():
         """K2 outputs -> labels -> K4 statistics; ONE all-reduce carries refit statistics + inlier counts"""
+        b = state["cur"]
         ctx.labels_from_best(fused["best"], labels)                                          # -1 = outlier
         d_ref.copy_(d_hyp)
-        ctx.refit_haf_accumulate(d_pts, d_aff, labels, K_HYP, out=acc)                       # K4 statistics
+        ctx.refit_haf_accumulate(d_pts, d_aff, labels, K_HYP, out=acc2[b])                   # K4 statistics
         if world > 1:
-            ctx.pack_inlier_counts(fused["inliers"], acc)
-            dist.all_reduce(acc)
-            ctx.pack_inlier_counts(fused["inliers"], acc, unpack=True)
-        ctx.refit_haf_solve(acc, d_ref)                                                      # K4 solves
+            ctx.pack_inlier_counts(fused["inliers"], acc2[b])
+            handle = dist.all_reduce(acc2[b], async_op=True)
+            finish_pending()                                                                 # previous step's reduction
+            state["pending"] = (handle, b)
+            state["cur"] = b ^ 1
+        else:
+            ctx.refit_haf_solve(acc2[b], d_ref)                                              # K4 solves
 
     def hot_pass(ev=None):
+        bc = dist.broadcast(d_hyp, src=0, async_op=True) if world > 1 else None              # overlaps K1
         ctx.haf_hypotheses(d_pts, d_aff, out=d_hyp_pt)                                      # K1
-        if world > 1:
-            dist.broadcast(d_hyp, src=0)
+        if bc is not None:
+            bc.wait()
         if ev is not None:
             ev[0].record()
         ctx.data_cost_fused(d_pts, d_hyp, kmax=0, want_list=False, out=fused)                # K2
@@ -224,6 +245,7 @@ def main():
         main.wait_event(ev_aff)
         ctx.haf_hypotheses(d_pts, d_aff, out=d_hyp_pt)                                      # K1
         stats_and_refit()                                                                    # K4 (+ all-reduce)
+        finish_pending()                                                                     # e2e: results of THIS step
         h_labels.copy_(labels, non_blocking=True)                                            # D2H results
         h_ref.copy_(d_ref, non_blocking=True)
         torch.cuda.synchronize()
@@ -237,6 +259,7 @@ def main():
     for i in range(args.warmup):
         hot_pass(k2_ev[i])
         flush.zero_()
+    finish_pending()
     barrier()
     sampler = ClockSampler(local)
     sampler.start()
@@ -246,6 +269,7 @@ def main():
     for i in range(args.steps):
         hot_pass(k2_ev[args.warmup + i])
         flush.zero_()  # L2 flush between timed iterations (inside the timed region; ~40 us per step)
+    finish_pending()
     t1.record()
     barrier()
     sampler.stop_flag = True
