@@ -18,60 +18,9 @@
 // per-site sparse lists / argmin / per-hypothesis inlier counters.
 // ============================================================================
 #include "common.cuh"
+#include "k2_device.cuh"
 
 namespace mh {
-
-typedef unsigned long long u64;
-
-// ---- packed f32x2 helpers --------------------------------------------------
-__device__ __forceinline__ u64 pk(float lo, float hi) {
-  u64 r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-  return r;
-}
-__device__ __forceinline__ void upk(u64 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
-__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) {
-  u64 d;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-  return d;
-}
-__device__ __forceinline__ u64 mul2(u64 a, u64 b) {
-  u64 d;
-  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-  return d;
-}
-__device__ __forceinline__ float rcp_approx(float x) {
-  float r;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-  return r;
-}
-__device__ __forceinline__ float min3(float a, float b, float c) {
-  float r;
-  asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
-  return r;
-}
-
-// squared reprojection residual of one correspondence under one homography
-// (MultiH.cpp:491-498), normalised units; one reciprocal, two FMAs for the divide.
-__device__ __forceinline__ float residual(const float h[9], float x, float y, float x2, float y2) {
-  const float s = fmaf(h[6], x, fmaf(h[7], y, h[8]));
-  const float xn = fmaf(h[0], x, fmaf(h[1], y, h[2]));
-  const float yn = fmaf(h[3], x, fmaf(h[4], y, h[5]));
-  const float r = rcp_approx(s);
-  const float dx = fmaf(xn, r, -x2);
-  const float dy = fmaf(yn, r, -y2);
-  return fmaf(dx, dx, dy * dy);
-}
-
-// integer data cost of an in-range residual: round(lam * (1 - d2/T)), C round()
-// on a non-negative value == floor(v + 0.5) (MultiH.cpp:501-502).
-__device__ __forceinline__ int cost_in_range(float d2, const CostParams& cp) {
-  const float v = fmaf(-cp.lam * cp.inv_T, d2, cp.lam);
-  return (int)floorf(fmaxf(v, 0.f) + 0.5f);
-}
-__device__ __forceinline__ int cost_of(float d2, const CostParams& cp) {
-  return (d2 < cp.T) ? cost_in_range(d2, cp) : cp.cost_far;  // NaN compares false -> far, as in the reference
-}
 
 // ============================================================================
 // Dense matrix: out[p*(K+1) + l], l = 0 outlier label (GCoptimization.h:339).
@@ -293,20 +242,6 @@ cost_fused_kernel(const float4* __restrict__ pts, long long N, const float* __re
 // Issue budget per residual: 5 FFMA2 + 1 MUFU + ~0.3 LDS + 1 (argmin filter) + 2
 // (inlier) ~ 9.5 slots against ~11 FMA-pipe cycles for the 5 FFMA2.
 // ----------------------------------------------------------------------------
-struct FastOut {
-  u64* best;             // [N] packed (cost << 32 | label), pre-initialised to (cost_outlier << 32 | 0)
-  int32_t* inlier_count; // [K]
-};
-
-__device__ __forceinline__ void fast_thresholds(int best_cost, const CostParams& cp, float& negmid, float& half) {
-  // a residual improves on best_cost iff cost(d2) <= best_cost - 1  <=>  d2 > T * (lam + 0.5 - best_cost) / lam
-  float lo = cp.T * (cp.lam + 0.5f - (float)best_cost) * (1.0f / cp.lam);
-  lo = fmaxf(lo, 0.f) * 0.9999f - 1e-12f;      // conservative: false positives are rejected by the exact update
-  const float hi = cp.T * 1.0001f;
-  negmid = -0.5f * (lo + hi);
-  half = 0.5f * (hi - lo);
-}
-
 // v3 register tile: 4 correspondences per thread x 2 hypothesis pairs (4 hypotheses) per iteration.
 constexpr int FAST_P = 4;  // <= 1024 correspondences per CTA => per-CTA inlier counts fit 16 bits
 
@@ -662,17 +597,6 @@ cost_argmin_t_kernel(const float4* __restrict__ pts, long long N, const u64* __r
 // (rare) update path; per-hypothesis inlier bits are funnel-shifted into masks and added to shared counters once per
 // 8-hypothesis block.
 // ----------------------------------------------------------------------------
-__device__ __forceinline__ unsigned to_tf32(float x) {
-  unsigned r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return r;
-}
-__device__ __forceinline__ void mma_tf32(float (&d)[4], const unsigned (&a)[4], unsigned b0, unsigned b1) {
-  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%10,%10,%10};"
-               : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3])
-               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1), "f"(0.f));
-}
-
 constexpr int MMA_THREADS = 256;
 constexpr int MMA_CH = 512;  // hypotheses staged per chunk (48 KB of split fragments)
 
@@ -860,6 +784,9 @@ __global__ void fused_init_kernel(long long N, int K, int32_t* list_count, u64* 
   if (inlier_count && i < K) inlier_count[i] = 0;
 }
 
+mh_status launch_cost_argmin_tc(mh_ctx* ctx, const float4* d_pts, int64_t N, const float* d_hyp, int K, const CostParams& cp,
+                                const FastOut& fo, int config);  // k2_mma.cu
+
 int g_fused_variant = 1;  // 1 = packed FFMA2 (default), 0 = scalar FFMA (A/B evidence)
 int g_fast_config = 5;    // (threads/CTA, CTAs/SM, chunk pairs) of the fast path, see launch_cost_fused; 5 = 128 x 7 x 128 (default)
 
@@ -943,6 +870,7 @@ mh_status launch_cost_fused(mh_ctx* ctx, const float4* d_pts, int64_t N, const f
       }
       return MH_OK;
     };
+    if (g_fast_config >= 30 && g_fast_config < 60) return launch_cost_argmin_tc(ctx, d_pts, N, d_hyp, K, cp, fo, g_fast_config);
     switch (g_fast_config) {
       case 20: MH_TRY(launch_m(cost_argmin_mma_kernel<true, 2, 2>, cost_argmin_mma_kernel<false, 2, 2>, 2)); break;
       case 21: MH_TRY(launch_m(cost_argmin_mma_kernel<true, 3, 2>, cost_argmin_mma_kernel<false, 3, 2>, 2)); break;

@@ -8,6 +8,7 @@ ctx = m.Context(); ctx.set_geometry(sc.F, sc.pts)
 d_pts, d_aff = ctx.upload(sc.pts, sc.aff)
 p_pts, p_aff = ctx.upload(sc.pts[pick], sc.aff[pick])
 d_hyp = torch.cat([ctx.hypotheses_from_host(sc.planes), ctx.haf_hypotheses(p_pts, p_aff)]).contiguous()
+if os.environ.get('MH_FAST_CONFIG'): ctx.set_fast_config(int(os.environ['MH_FAST_CONFIG']))
 o = {}
 for _ in range(3):
     o = ctx.data_cost_fused(d_pts, d_hyp, kmax=0, want_list=False, out=o)
