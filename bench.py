@@ -160,6 +160,8 @@ def main():
     lo, hi = m.dist.shard_range(n_total, rank, world)
     n_loc = hi - lo
     ctx = m.Context(device=local)
+    if os.environ.get("MH_FAST_CONFIG"):  # K2 variant override for tuning runs (default: the library's)
+        ctx.set_fast_config(int(os.environ["MH_FAST_CONFIG"]))
     ctx.set_geometry(sc.F, sc.pts)  # same strided sample on every rank -> identical normalisation
     h_pts = torch.from_numpy(sc.pts[lo:hi]).pin_memory()
     h_aff = torch.from_numpy(sc.aff[lo:hi]).pin_memory()

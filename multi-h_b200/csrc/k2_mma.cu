@@ -85,18 +85,35 @@ struct Acc {
 };
 
 // WARPS warps per CTA, each owning 16 * PB correspondences; CH hypotheses per staged chunk.
-template <bool COUNT_INLIERS, int WARPS, int MINB, int PB, int CH, bool PIPE>
+// DEFER (v7): candidates that pass the interval test are not evaluated on the spot; they are appended to a per-warp
+// queue in shared memory ((row, hypothesis pair), one ballot + one STS per row slot) and the queue is drained by the
+// whole warp — one candidate per lane: exact FP32 re-evaluation, shared-memory atomicMin on the row's packed
+// (cost, label) — whenever QTHR entries are waiting.  The rows' filters are refreshed from shared memory after a drain;
+// until then they are stale, i.e. looser, so no candidate is missed and the result is unchanged.  v6 spent a third of
+// its instructions in the warp-serial per-slot update; the queue makes that work lane-parallel.
+// The queue is checked once per two 8-hypothesis blocks, so it holds QTHR waiting entries plus whatever two epilogues can
+// add (2 blocks x 2 PB row slots x 32 lanes): no capacity test on the push path, and one inlined copy of the drain.
+__host__ __device__ constexpr int queue_capacity(int PB) { return 32 + 2 * 2 * PB * 32; }
+
+template <bool COUNT_INLIERS, int WARPS, int MINB, int PB, int CH, bool PIPE, int QTHR = 0>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
 cost_argmin_tc_kernel(const float4* __restrict__ pts, long long N, const float* __restrict__ hyp,
                       const float2* __restrict__ hsplit, int K, int k_per_block, CostParams cp, FastOut o,
                       int use_atomic_best) {
   constexpr int THREADS = WARPS * 32;
   constexpr unsigned CHUNK_BYTES = CH * 96;
+  constexpr bool DEFER = QTHR > 0;
+  constexpr int QCAP = queue_capacity(PB);
+  static_assert(QTHR <= 32, "queue_capacity() assumes at most 32 waiting entries");
   // dynamic shared memory: [2][CH][3][4] float2 split fragments | [2][WARPS][CH] u8 per-warp inlier counts | 2 mbarriers
+  //                        | DEFER: [WARPS][QCAP] candidate queues | [WARPS][16 PB] packed (cost << 16 | label) per row
   extern __shared__ __align__(128) unsigned char tc_smem[];
   float2* sB = reinterpret_cast<float2*>(tc_smem);
   unsigned char* sCnt = tc_smem + 2 * CHUNK_BYTES;
   unsigned long long* bars = reinterpret_cast<unsigned long long*>(tc_smem + 2 * CHUNK_BYTES + 2 * WARPS * CH);
+  unsigned* sQ = reinterpret_cast<unsigned*>(tc_smem + 2 * CHUNK_BYTES + 2 * WARPS * CH + 16) + (threadIdx.x >> 5) * (QCAP + 16 * PB);
+  unsigned* sBest = sQ + QCAP;
+  int qcnt = 0;   // warp-uniform
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
   constexpr int PTS_PER_WARP = 16 * PB, TILE = WARPS * PTS_PER_WARP;
@@ -139,6 +156,10 @@ cost_argmin_tc_kernel(const float4* __restrict__ pts, long long N, const float* 
       A[pb][2 + r] = t == 0 ? xhi : t == 1 ? yhi : t == 2 ? ylo : one;  // a2 / a3: k = t + 4
     }
   const u64 ONE2 = pk(1.f, 1.f);
+  if (DEFER) {
+    for (int i = lane; i < 16 * PB; i += 32) sBest[i] = best_init;
+    __syncwarp();
+  }
 
   auto mma_block = [&](const float2* bp, Acc<PB>& a) {   // bp -> this thread's fragment of an 8-hypothesis block
     const float2 bs = bp[0], bx = bp[4], by = bp[8];
@@ -182,9 +203,49 @@ cost_argmin_tc_kernel(const float4* __restrict__ pts, long long N, const float* 
     }
   };
 
+  // DEFER: the whole warp evaluates the queued candidates, one per lane, then every thread refreshes its rows' filters
+  auto drain = [&]() {
+    __syncwarp();
+    for (int i = lane; i < qcnt; i += 32) {
+      const unsigned e = sQ[i];
+      const int row = (int)(e >> 24), ih0 = (int)(e & 0xffffffu);
+      const float4 q = __ldg(pts + tile0 + row);   // < N: padding rows never raise a flag
+      float ha[9], hb[9];
+      {
+        const float4* hp = reinterpret_cast<const float4*>(hyp + (size_t)min(ih0, K - 1) * 12);
+        const float4 u = __ldg(hp), v = __ldg(hp + 1), w = __ldg(hp + 2);
+        ha[0] = u.x; ha[1] = u.y; ha[2] = u.z; ha[3] = u.w; ha[4] = v.x; ha[5] = v.y; ha[6] = v.z; ha[7] = v.w; ha[8] = w.x;
+      }
+      {
+        const float4* hp = reinterpret_cast<const float4*>(hyp + (size_t)min(ih0 + 1, K - 1) * 12);
+        const float4 u = __ldg(hp), v = __ldg(hp + 1), w = __ldg(hp + 2);
+        hb[0] = u.x; hb[1] = u.y; hb[2] = u.z; hb[3] = u.w; hb[4] = v.x; hb[5] = v.y; hb[6] = v.z; hb[7] = v.w; hb[8] = w.x;
+      }
+      const float da = residual(ha, q.x, q.y, q.z, q.w);
+      const float db = residual(hb, q.x, q.y, q.z, q.w);
+      unsigned mine = 0xffffffffu;
+      if (ih0 < kend && da < cp.T) mine = ((unsigned)cost_in_range(da, cp) << 16) | (unsigned)(ih0 + 1);
+      if (ih0 + 1 < kend && db < cp.T) mine = min(mine, ((unsigned)cost_in_range(db, cp) << 16) | (unsigned)(ih0 + 2));
+      if (mine != 0xffffffffu) atomicMin(sBest + row, mine);   // (cost, label) packed: ties keep the lowest label
+    }
+    __syncwarp();
+#pragma unroll
+    for (int pb = 0; pb < PB; ++pb)
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const unsigned b = sBest[pb * 16 + g + 8 * r];
+        if (b < BEST[pb][r]) {
+          BEST[pb][r] = b;
+          fast_thresholds((int)(b >> 16), cp, NEGMID[pb][r], HALF[pb][r]);
+          C[pb][r] = -NEGMID[pb][r] - cp.thr2;
+        }
+      }
+    qcnt = 0;
+  };
+
   // FP32 epilogue of one 8-hypothesis block; returns the thread's inlier counts {popc(col 2t), popc(col 2t+1)} in two bytes
   auto epilogue = [&](const Acc<PB>& a, int ih_block) -> unsigned {
-    unsigned mask0 = 0u, mask1 = 0u;
+    unsigned mask0 = 0u, mask1 = 0u;   // v6: shifted-in sign bits; DEFER: running counts (LEA.HI, no POPC)
     bool flag[PB][2];
     bool any = false;
 #pragma unroll
@@ -200,8 +261,13 @@ cost_argmin_tc_kernel(const float4* __restrict__ pts, long long N, const float* 
         if (COUNT_INLIERS) {
           float va, vb;
           upk(fma2(tt, ONE2, pk(C[pb][r], C[pb][r])), va, vb);  // d2 - thr2: sign bit = inlier
-          mask0 = __funnelshift_l(__float_as_uint(va), mask0, 1);
-          mask1 = __funnelshift_l(__float_as_uint(vb), mask1, 1);
+          if (DEFER) {
+            mask0 += __float_as_uint(va) >> 31;
+            mask1 += __float_as_uint(vb) >> 31;
+          } else {
+            mask0 = __funnelshift_l(__float_as_uint(va), mask0, 1);
+            mask1 = __funnelshift_l(__float_as_uint(vb), mask1, 1);
+          }
         }
         flag[pb][r] = fminf(fabsf(ta), fabsf(tb)) < HALF[pb][r];
         any = any || flag[pb][r];
@@ -211,10 +277,22 @@ cost_argmin_tc_kernel(const float4* __restrict__ pts, long long N, const float* 
       for (int pb = 0; pb < PB; ++pb)
 #pragma unroll
         for (int r = 0; r < 2; ++r)
-          if (__any_sync(0xffffffffu, flag[pb][r]))
+        {
+          if (DEFER) {
+            const unsigned m = __ballot_sync(0xffffffffu, flag[pb][r]);
+            if (m) {
+              const int n = __popc(m);
+              if (flag[pb][r])
+                sQ[qcnt + __popc(m & ((1u << lane) - 1u))] = ((unsigned)(pb * 16 + g + 8 * r) << 24) | (unsigned)(ih_block + 2 * t);
+              qcnt += n;
+            }
+          } else if (__any_sync(0xffffffffu, flag[pb][r])) {
             update_slot(pb, r, flag[pb][r], ih_block + 2 * t, NEGMID[pb][r], HALF[pb][r], C[pb][r], BEST[pb][r]);
+          }
+        }
     }
-    return COUNT_INLIERS ? (__popc(mask0) | (__popc(mask1) << 8)) : 0u;
+    if (!COUNT_INLIERS) return 0u;
+    return DEFER ? (mask0 | (mask1 << 8)) : (__popc(mask0) | (__popc(mask1) << 8));
   };
 
   for (int ci = 0; ci < nchunks; ++ci) {
@@ -233,6 +311,32 @@ cost_argmin_tc_kernel(const float4* __restrict__ pts, long long N, const float* 
 
     Acc<PB> acc0, acc1;
     if (PIPE) mma_block(bp, acc0);
+    if (DEFER) {
+      // Two epilogues per loop trip.  ptxas folds a broadcast constant (-x2, -y2, -mid, mid - thr2) into FFMA2's scalar-
+      // operand form only when its {c, c} pack has a single use; with two uses it rebuilds register pairs in the loop
+      // (1.5 MOVs per residual, measured).  The empty asm between the two epilogues makes the second block's constants
+      // formally new values, so each pack keeps a single use — no instruction is emitted for it.
+#pragma unroll 1
+      for (int hb = 0; hb < NBLK; hb += 2) {
+        mma_block(bp + hb * 96, acc0);
+        unsigned packed = epilogue(acc0, c0 + hb * 8);
+#pragma unroll
+        for (int pb = 0; pb < PB; ++pb)
+#pragma unroll
+          for (int r = 0; r < 2; ++r)
+            asm volatile("" : "+f"(NX2[pb][r]), "+f"(NY2[pb][r]), "+f"(NEGMID[pb][r]), "+f"(C[pb][r]));
+        mma_block(bp + (hb + 1) * 96, acc0);
+        packed |= epilogue(acc0, c0 + hb * 8 + 8) << 16;
+        if (qcnt >= QTHR) drain();
+        if (COUNT_INLIERS) {
+          packed += __shfl_xor_sync(0xffffffffu, packed, 4);
+          packed += __shfl_xor_sync(0xffffffffu, packed, 8);
+          packed += __shfl_xor_sync(0xffffffffu, packed, 16);
+          *reinterpret_cast<unsigned short*>(cw + hb * 8) = (unsigned short)packed;
+          *reinterpret_cast<unsigned short*>(cw + hb * 8 + 8) = (unsigned short)(packed >> 16);
+        }
+      }
+    } else {
 #pragma unroll 1
     for (int hb = 0; hb < NBLK; hb += 2) {
       unsigned packed;
@@ -258,6 +362,7 @@ cost_argmin_tc_kernel(const float4* __restrict__ pts, long long N, const float* 
         *reinterpret_cast<unsigned short*>(cw + hb * 8 + 8) = (unsigned short)(packed >> 16);
       }
     }
+    }
     __syncthreads();   // every warp is done with fragment buffer buf; its counters are complete
     if (COUNT_INLIERS) {
       const int nh = min(CH, kend - c0);
@@ -270,6 +375,7 @@ cost_argmin_tc_kernel(const float4* __restrict__ pts, long long N, const float* 
       }
     }
   }
+  if (DEFER && qcnt > 0) drain();
   if (o.best && t == 0) {  // the quad holds identical state: lane t == 0 writes
 #pragma unroll
     for (int pb = 0; pb < PB; ++pb)
@@ -286,7 +392,7 @@ cost_argmin_tc_kernel(const float4* __restrict__ pts, long long N, const float* 
   }
 }
 
-template <bool COUNT_INLIERS, int WARPS, int MINB, int PB, int CH, bool PIPE>
+template <bool COUNT_INLIERS, int WARPS, int MINB, int PB, int CH, bool PIPE, int QTHR = 0>
 static mh_status launch_tc(mh_ctx* ctx, const float4* d_pts, int64_t N, const float* d_hyp, int K, const CostParams& cp,
                            const FastOut& fo) {
   const int want = 2 * ctx->sm_count;
@@ -303,8 +409,8 @@ static mh_status launch_tc(mh_ctx* ctx, const float4* d_pts, int64_t N, const fl
   float2* d_split = (float2*)ctx->scratch;
   split_hyp_tf32_kernel<<<(unsigned)((Kpad + 127) / 128), 128, 0, ctx->stream>>>(d_hyp, K, Kpad, (float4*)d_split);
   MH_LAUNCHED(ctx, "split_hyp_tf32_kernel");
-  const size_t smem = 2 * (size_t)CH * 96 + 2 * (size_t)WARPS * CH + 16;
-  auto kern = cost_argmin_tc_kernel<COUNT_INLIERS, WARPS, MINB, PB, CH, PIPE>;
+  const size_t smem = 2 * (size_t)CH * 96 + 2 * (size_t)WARPS * CH + 16 + (QTHR > 0 ? (size_t)WARPS * (queue_capacity(PB) + 16 * PB) * 4 : 0);
+  auto kern = cost_argmin_tc_kernel<COUNT_INLIERS, WARPS, MINB, PB, CH, PIPE, QTHR>;
   MH_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<dim3(tiles, (unsigned)ks), WARPS * 32, smem, ctx->stream>>>(d_pts, N, d_hyp, d_split, K, kpb, cp, fo, ks > 1);
   MH_LAUNCHED(ctx, "cost_argmin_tc_kernel");
@@ -315,10 +421,10 @@ static mh_status launch_tc(mh_ctx* ctx, const float4* d_pts, int64_t N, const fl
 mh_status launch_cost_argmin_tc(mh_ctx* ctx, const float4* d_pts, int64_t N, const float* d_hyp, int K, const CostParams& cp,
                                 const FastOut& fo, int config) {
   const bool cnt = fo.inlier_count != nullptr;
-#define TC_CASE(id, WARPS, MINB, PB, CH, PIPE)                                                      \
-  case id:                                                                                          \
-    return cnt ? launch_tc<true, WARPS, MINB, PB, CH, PIPE>(ctx, d_pts, N, d_hyp, K, cp, fo)        \
-               : launch_tc<false, WARPS, MINB, PB, CH, PIPE>(ctx, d_pts, N, d_hyp, K, cp, fo);
+#define TC_CASE(id, WARPS, MINB, PB, CH, PIPE, ...)                                                              \
+  case id:                                                                                                       \
+    return cnt ? launch_tc<true, WARPS, MINB, PB, CH, PIPE, ##__VA_ARGS__>(ctx, d_pts, N, d_hyp, K, cp, fo)      \
+               : launch_tc<false, WARPS, MINB, PB, CH, PIPE, ##__VA_ARGS__>(ctx, d_pts, N, d_hyp, K, cp, fo);
   switch (config) {   // (warps per CTA, CTAs per SM, 16-row blocks per warp, hypotheses per chunk, explicit pipeline)
     TC_CASE(30, 8, 3, 2, 256, false)
     TC_CASE(31, 8, 2, 2, 256, true)
@@ -337,6 +443,22 @@ mh_status launch_cost_argmin_tc(mh_ctx* ctx, const float4* d_pts, int64_t N, con
     TC_CASE(44, 4, 6, 2, 64, false)
     TC_CASE(45, 4, 4, 3, 128, false)
     TC_CASE(46, 2, 8, 3, 64, false)
+    // v7: deferred candidate queue (last argument = drain threshold)
+    TC_CASE(50, 4, 7, 2, 128, false, 24)
+    TC_CASE(51, 4, 8, 2, 128, false, 24)
+    TC_CASE(52, 4, 6, 2, 128, false, 24)
+    TC_CASE(53, 8, 3, 2, 256, false, 24)
+    TC_CASE(54, 8, 4, 2, 128, false, 24)
+    TC_CASE(55, 4, 5, 3, 128, false, 24)
+    TC_CASE(56, 4, 4, 4, 128, false, 24)
+    TC_CASE(57, 4, 4, 4, 256, false, 24)
+    TC_CASE(58, 8, 2, 4, 512, false, 24)
+    TC_CASE(59, 4, 5, 3, 256, false, 24)
+    TC_CASE(60, 8, 4, 2, 256, false, 24)
+    TC_CASE(61, 4, 6, 3, 128, false, 24)
+    TC_CASE(62, 8, 3, 3, 256, false, 24)
+    TC_CASE(63, 4, 8, 2, 128, false, 32)
+    TC_CASE(64, 4, 8, 2, 64, false, 24)
     default: return fail(ctx, MH_EINVAL, "unknown tensor-core fast-path config");
   }
 #undef TC_CASE

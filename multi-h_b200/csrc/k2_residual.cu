@@ -870,7 +870,7 @@ mh_status launch_cost_fused(mh_ctx* ctx, const float4* d_pts, int64_t N, const f
       }
       return MH_OK;
     };
-    if (g_fast_config >= 30 && g_fast_config < 60) return launch_cost_argmin_tc(ctx, d_pts, N, d_hyp, K, cp, fo, g_fast_config);
+    if (g_fast_config >= 30 && g_fast_config < 100) return launch_cost_argmin_tc(ctx, d_pts, N, d_hyp, K, cp, fo, g_fast_config);
     switch (g_fast_config) {
       case 20: MH_TRY(launch_m(cost_argmin_mma_kernel<true, 2, 2>, cost_argmin_mma_kernel<false, 2, 2>, 2)); break;
       case 21: MH_TRY(launch_m(cost_argmin_mma_kernel<true, 3, 2>, cost_argmin_mma_kernel<false, 3, 2>, 2)); break;
