@@ -322,7 +322,9 @@ def main():
         except Exception:
             traffic = None
     roofline = {"bound": "fp32", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                "traffic": traffic, "kernel": "cost_argmin_kernel",
+                "traffic": traffic,
+                "kernel": ("cost_argmin_tc_kernel" if ctx.get_fast_config() >= 30 else "cost_argmin_kernel")
+                          + f" (fast config {ctx.get_fast_config()})",
                 "algorithmic": f"{FLOP_PER_RESIDUAL} flop/residual x {n_loc} x {K_HYP} per launch",
                 "kernel_ms": k2_ms, "kernel_share_of_step": k2_ms / ms_per_step,
                 "peak_source": "measured in this run: dependent-FFMA probe (mh_diag_fp32_peak), "

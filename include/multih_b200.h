@@ -224,6 +224,7 @@ mh_status mh_diag_set_fused_variant(mh_ctx* ctx, int32_t variant);
 /* K2 fast path launch shape (threads/CTA x CTAs/SM): 0 = 256x3, 1 = 256x2, 2 = 256x4, 3 = 128x5, 4 = 128x6,
  * 5 = 128x7 (default), 6 = 128x4 — tuning aid. */
 mh_status mh_diag_set_fast_config(mh_ctx* ctx, int32_t config);
+int32_t mh_diag_get_fast_config(mh_ctx* ctx);
 
 #ifdef __cplusplus
 }

@@ -65,8 +65,11 @@ struct FastOut {
 __device__ __forceinline__ void fast_thresholds(int best_cost, const CostParams& cp, float& negmid, float& half) {
   // a residual improves on best_cost iff cost(d2) <= best_cost - 1  <=>  d2 > T * (lam + 0.5 - best_cost) / lam
   float lo = cp.T * (cp.lam + 0.5f - (float)best_cost) * (1.0f / cp.lam);
-  lo = fmaxf(lo, 0.f) * 0.9999f - 1e-12f;      // conservative: false positives are rejected by the exact update
-  const float hi = cp.T * 1.0001f;
+  // conservative by 1e-3 (relative): the filter sees residuals whose rounding differs from the exact FP32 sequence (folded
+  // constants; in the tensor-core kernels 3xTF32 products of hypotheses with |h_i| <= 4 |h_8|, worth <~ 2e-4); false
+  // positives are rejected by the exact update
+  lo = fmaxf(lo, 0.f) * 0.999f - 1e-12f;
+  const float hi = cp.T * 1.001f;
   negmid = -0.5f * (lo + hi);
   half = 0.5f * (hi - lo);
 }

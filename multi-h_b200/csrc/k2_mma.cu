@@ -28,15 +28,32 @@ namespace mh {
 // hypotheses [K][12] -> split B fragments [Kpad][3][4] float2 (96 B per hypothesis):
 //   [hyp][s|xn|yn][t] = {B[t][hyp], B[t+4][hyp]},  B[k] = [ahi, bhi, chi, ahi, alo, blo, bhi, clo]
 // against A[k] = [xhi, yhi, 1, xlo, xhi, yhi, ylo, 1].  Rows >= K are "far" (residual ~1e36: never a hit, never an inlier).
-__global__ void split_hyp_tf32_kernel(const float* __restrict__ hyp, int K, int Kpad, float4* __restrict__ out) {
+//
+// "Wild" hypotheses — some |h_i| > WILD_RATIO |h_8|, or non-finite entries (HAF estimates of outlier correspondences) —
+// are kept off the tensor cores: the absolute error of a 3xTF32 product grows with |h_i| while the argmin filter's margin
+// is relative to d2, so for them the filter could miss a record-breaking candidate.  They become "far" columns here, are
+// appended to wild_list, and cost_argmin_wild_kernel evaluates them afterwards with the exact FP32 sequence.
+constexpr float WILD_RATIO = 4.f;
+
+__global__ void split_hyp_tf32_kernel(const float* __restrict__ hyp, int K, int Kpad, float4* __restrict__ out,
+                                      int* __restrict__ wild_count, int* __restrict__ wild_list) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= Kpad) return;
   float h[9];
-  if (j < K) {
+  bool far = j >= K;
+  if (!far) {
     const float4* p = reinterpret_cast<const float4*>(hyp + (size_t)j * 12);
     const float4 u = p[0], v = p[1], w = p[2];
     h[0] = u.x; h[1] = u.y; h[2] = u.z; h[3] = u.w; h[4] = v.x; h[5] = v.y; h[6] = v.z; h[7] = v.w; h[8] = w.x;
-  } else {
+    float mx = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) mx = fmaxf(mx, fabsf(h[k]));
+    if (!(mx <= WILD_RATIO * fabsf(h[8])) || !(fabsf(h[8]) < 3.0e38f)) {   // also catches NaN / Inf
+      far = true;
+      wild_list[atomicAdd(wild_count, 1)] = j;
+    }
+  }
+  if (far) {
     h[0] = h[1] = h[3] = h[4] = h[6] = h[7] = 0.f; h[2] = h[5] = 1e18f; h[8] = 1.f;
   }
 #pragma unroll
@@ -135,7 +152,15 @@ cost_argmin_tc_kernel(const float4* __restrict__ pts, long long N, const float* 
 
   // ---- per-thread correspondence state: rows g and g+8 of each of the warp's PB 16-row blocks ----------------------
   unsigned A[PB][4];
-  float NX2[PB][2], NY2[PB][2], NEGMID[PB][2], HALF[PB][2], C[PB][2];
+  // CM: the constant that turns the folded sum into d2 - mid for the argmin interval test.  With inlier counting the fold
+  // is d2 - thr2 (its sign IS the inlier flag, independent of the row's filter state, hence of how rows are grouped into
+  // warps) and CM = thr2 - mid is added afterwards; without it -mid is folded directly.
+  float NX2[PB][2], NY2[PB][2], CM[PB][2], HALF[PB][2];
+  auto set_filter = [&](int best_cost, float& cm, float& half) {
+    float negmid;
+    fast_thresholds(best_cost, cp, negmid, half);
+    cm = COUNT_INLIERS ? cp.thr2 + negmid : negmid;
+  };
   unsigned BEST[PB][2];
   const unsigned best_init = ((unsigned)min(cp.cost_outlier, 0xffff) << 16);
 #pragma unroll
@@ -146,16 +171,15 @@ cost_argmin_tc_kernel(const float4* __restrict__ pts, long long N, const float* 
       const float4 q = pts[idx < N ? idx : N - 1];
       NX2[pb][r] = -q.z; NY2[pb][r] = -q.w;
       BEST[pb][r] = best_init;
-      fast_thresholds(cp.cost_outlier, cp, NEGMID[pb][r], HALF[pb][r]);
-      C[pb][r] = -NEGMID[pb][r] - cp.thr2;
-      if (idx >= N) { HALF[pb][r] = -1.f; C[pb][r] = 3.0e38f; }
+      set_filter(cp.cost_outlier, CM[pb][r], HALF[pb][r]);
+      if (idx >= N) { HALF[pb][r] = -1.f; NX2[pb][r] = NY2[pb][r] = 1e18f; }   // padding rows: d2 ~ 1e36, never a hit
       const unsigned xhi = to_tf32(q.x), yhi = to_tf32(q.y);
       const unsigned xlo = to_tf32(q.x - __uint_as_float(xhi)), ylo = to_tf32(q.y - __uint_as_float(yhi));
       const unsigned one = 0x3f800000u;
       A[pb][r] = t == 0 ? xhi : t == 1 ? yhi : t == 2 ? one : xlo;      // a0 (row g) / a1 (row g+8): k = t
       A[pb][2 + r] = t == 0 ? xhi : t == 1 ? yhi : t == 2 ? ylo : one;  // a2 / a3: k = t + 4
     }
-  const u64 ONE2 = pk(1.f, 1.f);
+  const u64 ONE2 = pk(1.f, 1.f), NEGTHR2 = pk(-cp.thr2, -cp.thr2);
   if (DEFER) {
     for (int i = lane; i < 16 * PB; i += 32) sBest[i] = best_init;
     __syncwarp();
@@ -173,7 +197,7 @@ cost_argmin_tc_kernel(const float4* __restrict__ pts, long long N, const float* 
 
   // exact re-evaluation of hypotheses (ih0, ih0 + 1) for row slot (pb, r): entered warp-uniformly; lanes without a
   // candidate only take part in the quad reduction
-  auto update_slot = [&](int pb, int r, bool mine_flag, int ih0, float& negmid, float& half, float& c, unsigned& best) {
+  auto update_slot = [&](int pb, int r, bool mine_flag, int ih0, float& cm, float& half, unsigned& best) {
     unsigned mine = 0xffffffffu;
     if (mine_flag) {
       const long long idx = tile0 + pb * 16 + g + 8 * r;   // < N: padding rows never raise a flag
@@ -198,8 +222,7 @@ cost_argmin_tc_kernel(const float4* __restrict__ pts, long long N, const float* 
     mine = min(mine, __shfl_xor_sync(0xffffffffu, mine, 2));
     if (mine < best) {   // labels rise along the loop for a given correspondence: only strictly cheaper candidates matter
       best = mine;
-      fast_thresholds((int)(mine >> 16), cp, negmid, half);
-      c = -negmid - cp.thr2;
+      set_filter((int)(mine >> 16), cm, half);
     }
   };
 
@@ -236,8 +259,7 @@ cost_argmin_tc_kernel(const float4* __restrict__ pts, long long N, const float* 
         const unsigned b = sBest[pb * 16 + g + 8 * r];
         if (b < BEST[pb][r]) {
           BEST[pb][r] = b;
-          fast_thresholds((int)(b >> 16), cp, NEGMID[pb][r], HALF[pb][r]);
-          C[pb][r] = -NEGMID[pb][r] - cp.thr2;
+          set_filter((int)(b >> 16), CM[pb][r], HALF[pb][r]);
         }
       }
     qcnt = 0;
@@ -255,12 +277,12 @@ cost_argmin_tc_kernel(const float4* __restrict__ pts, long long N, const float* 
         const u64 rr = pk(rcp_approx(a.S[pb][2 * r]), rcp_approx(a.S[pb][2 * r + 1]));
         const u64 dx = fma2(pk(a.XN[pb][2 * r], a.XN[pb][2 * r + 1]), rr, pk(NX2[pb][r], NX2[pb][r]));
         const u64 dy = fma2(pk(a.YN[pb][2 * r], a.YN[pb][2 * r + 1]), rr, pk(NY2[pb][r], NY2[pb][r]));
-        const u64 tt = fma2(dx, dx, fma2(dy, dy, pk(NEGMID[pb][r], NEGMID[pb][r])));  // d2 - mid
         float ta, tb;
-        upk(tt, ta, tb);
         if (COUNT_INLIERS) {
+          const u64 vv = fma2(dx, dx, fma2(dy, dy, NEGTHR2));               // d2 - thr2: sign bit = inlier
+          upk(fma2(vv, ONE2, pk(CM[pb][r], CM[pb][r])), ta, tb);             // d2 - mid
           float va, vb;
-          upk(fma2(tt, ONE2, pk(C[pb][r], C[pb][r])), va, vb);  // d2 - thr2: sign bit = inlier
+          upk(vv, va, vb);
           if (DEFER) {
             mask0 += __float_as_uint(va) >> 31;
             mask1 += __float_as_uint(vb) >> 31;
@@ -268,6 +290,8 @@ cost_argmin_tc_kernel(const float4* __restrict__ pts, long long N, const float* 
             mask0 = __funnelshift_l(__float_as_uint(va), mask0, 1);
             mask1 = __funnelshift_l(__float_as_uint(vb), mask1, 1);
           }
+        } else {
+          upk(fma2(dx, dx, fma2(dy, dy, pk(CM[pb][r], CM[pb][r]))), ta, tb);   // d2 - mid
         }
         flag[pb][r] = fminf(fabsf(ta), fabsf(tb)) < HALF[pb][r];
         any = any || flag[pb][r];
@@ -287,7 +311,7 @@ cost_argmin_tc_kernel(const float4* __restrict__ pts, long long N, const float* 
               qcnt += n;
             }
           } else if (__any_sync(0xffffffffu, flag[pb][r])) {
-            update_slot(pb, r, flag[pb][r], ih_block + 2 * t, NEGMID[pb][r], HALF[pb][r], C[pb][r], BEST[pb][r]);
+            update_slot(pb, r, flag[pb][r], ih_block + 2 * t, CM[pb][r], HALF[pb][r], BEST[pb][r]);
           }
         }
     }
@@ -324,7 +348,7 @@ cost_argmin_tc_kernel(const float4* __restrict__ pts, long long N, const float* 
         for (int pb = 0; pb < PB; ++pb)
 #pragma unroll
           for (int r = 0; r < 2; ++r)
-            asm volatile("" : "+f"(NX2[pb][r]), "+f"(NY2[pb][r]), "+f"(NEGMID[pb][r]), "+f"(C[pb][r]));
+            asm volatile("" : "+f"(NX2[pb][r]), "+f"(NY2[pb][r]), "+f"(CM[pb][r]));
         mma_block(bp + (hb + 1) * 96, acc0);
         packed |= epilogue(acc0, c0 + hb * 8 + 8) << 16;
         if (qcnt >= QTHR) drain();
@@ -392,6 +416,40 @@ cost_argmin_tc_kernel(const float4* __restrict__ pts, long long N, const float* 
   }
 }
 
+// Exact FP32 pass over the wild hypotheses (a handful per thousand): one correspondence per thread, the dense kernel's
+// instruction sequence, merged into the tensor-core kernel's result with a 64-bit atomicMin on (cost << 32 | label) —
+// a total order, so the merged argmin is the same as a single pass over all hypotheses.
+__global__ void __launch_bounds__(256) cost_argmin_wild_kernel(const float4* __restrict__ pts, long long N,
+                                                                const float* __restrict__ hyp,
+                                                                const int* __restrict__ wild_count,
+                                                                const int* __restrict__ wild_list, CostParams cp, FastOut o) {
+  const int nw = *wild_count;
+  if (nw == 0) return;
+  const int lane = threadIdx.x & 31;
+  for (long long base = (long long)blockIdx.x * blockDim.x; base < N; base += (long long)gridDim.x * blockDim.x) {
+    const long long idx = base + threadIdx.x;
+    const bool live = idx < N;
+    const float4 q = pts[live ? idx : N - 1];
+    unsigned bc = (unsigned)cp.cost_outlier, bl = 0u;
+    for (int j = 0; j < nw; ++j) {
+      const int k = wild_list[j];
+      const float4* hp = reinterpret_cast<const float4*>(hyp + (size_t)k * 12);
+      const float4 u = __ldg(hp), v = __ldg(hp + 1), w = __ldg(hp + 2);
+      const float h[9] = {u.x, u.y, u.z, u.w, v.x, v.y, v.z, v.w, w.x};
+      const float d2 = residual(h, q.x, q.y, q.z, q.w);
+      if (live && d2 < cp.T) {
+        const unsigned c = (unsigned)cost_in_range(d2, cp);
+        if (c < bc || (c == bc && (unsigned)(k + 1) < bl)) { bc = c; bl = (unsigned)(k + 1); }   // list order is arbitrary
+      }
+      if (o.inlier_count) {
+        const unsigned m = __ballot_sync(0xffffffffu, live && d2 < cp.thr2);
+        if (lane == 0 && m) atomicAdd(o.inlier_count + k, __popc(m));
+      }
+    }
+    if (o.best && live && bl != 0u) atomicMin(o.best + idx, ((u64)bc << 32) | (u64)bl);
+  }
+}
+
 template <bool COUNT_INLIERS, int WARPS, int MINB, int PB, int CH, bool PIPE, int QTHR = 0>
 static mh_status launch_tc(mh_ctx* ctx, const float4* d_pts, int64_t N, const float* d_hyp, int K, const CostParams& cp,
                            const FastOut& fo) {
@@ -405,15 +463,23 @@ static mh_status launch_tc(mh_ctx* ctx, const float4* d_pts, int64_t N, const fl
   kpb = ((kpb + CH - 1) / CH) * CH;   // whole chunks per CTA
   ks = (K + kpb - 1) / kpb;
   const int Kpad = ks * kpb;
-  MH_TRY(ensure_scratch(ctx, (uint64_t)Kpad * 96));
+  // scratch: [Kpad x 96 B split fragments][wild count (16 B)][K wild indices]
+  MH_TRY(ensure_scratch(ctx, (uint64_t)Kpad * 96 + 16 + (uint64_t)K * 4));
   float2* d_split = (float2*)ctx->scratch;
-  split_hyp_tf32_kernel<<<(unsigned)((Kpad + 127) / 128), 128, 0, ctx->stream>>>(d_hyp, K, Kpad, (float4*)d_split);
+  int* d_wild_count = (int*)((char*)ctx->scratch + (size_t)Kpad * 96);
+  int* d_wild_list = d_wild_count + 4;
+  MH_CUDA(ctx, cudaMemsetAsync(d_wild_count, 0, 16, ctx->stream));
+  split_hyp_tf32_kernel<<<(unsigned)((Kpad + 127) / 128), 128, 0, ctx->stream>>>(d_hyp, K, Kpad, (float4*)d_split, d_wild_count,
+                                                                                d_wild_list);
   MH_LAUNCHED(ctx, "split_hyp_tf32_kernel");
   const size_t smem = 2 * (size_t)CH * 96 + 2 * (size_t)WARPS * CH + 16 + (QTHR > 0 ? (size_t)WARPS * (queue_capacity(PB) + 16 * PB) * 4 : 0);
   auto kern = cost_argmin_tc_kernel<COUNT_INLIERS, WARPS, MINB, PB, CH, PIPE, QTHR>;
   MH_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<dim3(tiles, (unsigned)ks), WARPS * 32, smem, ctx->stream>>>(d_pts, N, d_hyp, d_split, K, kpb, cp, fo, ks > 1);
   MH_LAUNCHED(ctx, "cost_argmin_tc_kernel");
+  const unsigned wild_grid = (unsigned)std::min<long long>((N + 255) / 256, 8LL * ctx->sm_count);
+  cost_argmin_wild_kernel<<<wild_grid, 256, 0, ctx->stream>>>(d_pts, N, d_hyp, d_wild_count, d_wild_list, cp, fo);
+  MH_LAUNCHED(ctx, "cost_argmin_wild_kernel");
   return MH_OK;
 }
 

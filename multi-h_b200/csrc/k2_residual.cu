@@ -788,7 +788,7 @@ mh_status launch_cost_argmin_tc(mh_ctx* ctx, const float4* d_pts, int64_t N, con
                                 const FastOut& fo, int config);  // k2_mma.cu
 
 int g_fused_variant = 1;  // 1 = packed FFMA2 (default), 0 = scalar FFMA (A/B evidence)
-int g_fast_config = 5;    // (threads/CTA, CTAs/SM, chunk pairs) of the fast path, see launch_cost_fused; 5 = 128 x 7 x 128 (default)
+int g_fast_config = 55;   // fast-path variant, see launch_cost_fused / launch_cost_argmin_tc; 55 = v7 tensor-core kernel, 4 warps x 5 CTAs/SM x 48 rows/warp (default); 5 = v3 FFMA2 kernel
 
 mh_status launch_cost_fused(mh_ctx* ctx, const float4* d_pts, int64_t N, const float* d_hyp, int K, int kmax,
                             uint32_t* d_list, int32_t* d_list_count, unsigned long long* d_best,

@@ -8,5 +8,5 @@ BEST=$(grep '^cfg' gpurun_out/tune.log | grep 'same best True' | sort -t' ' -k4 
 echo "best config: $BEST" >> gpurun_out/tune.log
 MH_FAST_CONFIG=$BEST timeout 400 ncu --set full --clock-control none --import-source on -k regex:cost_argmin -s 2 -c 1 \
   -o gpurun_out/k2_best -f python tools/ncu_k2.py 1048576 > gpurun_out/ncu_k2.log 2>&1
-MH_FAST_CONFIG=$BEST timeout 400 python bench.py > gpurun_out/bench.log 2> gpurun_out/bench.err
+timeout 400 python bench.py > gpurun_out/bench.log 2> gpurun_out/bench.err
 tail -3 gpurun_out/pytest.log; cat gpurun_out/tune.log; tail -2 gpurun_out/ncu_k2.log; cat gpurun_out/bench.log

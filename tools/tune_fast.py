@@ -13,7 +13,7 @@ N = 1 << 20
 scb = m.scenes.make_scene(N, 200, seed=0xB200 + 3)
 ctx = m.Context(); ctx.set_geometry(scb.F, scb.pts); pb, ab = ctx.upload(scb.pts, scb.aff)
 hb = ctx.haf_hypotheses(pb, ab)
-idx = torch.randint(0, N, (7992,), device="cuda")
+idx = torch.randint(0, N, (7992,), device="cuda", generator=torch.Generator("cuda").manual_seed(int(os.environ.get("TUNE_SEED", "4"))))
 hyp = torch.cat([ctx.hypotheses_from_host(scb.planes), hb[idx]]).contiguous()
 ctx.set_fused_variant(0)
 lst = ctx.data_cost_fused(pb, hyp, kmax=1)   # list kernel (scalar) as the cross-check
