@@ -331,30 +331,36 @@ def main():
                                f"scalar FFMA {peak_scalar:.1f} / packed FFMA2 {peak_packed:.1f} TFLOP/s; "
                                "MEASURED_PEAKS.json carries only HBM and bf16-tensor peaks; nominal 148 SM x 128 lanes x "
                                "2 x 1.965 GHz = 74.4"}
-    # the HBM-bound variant of the same kernel family (dense int16 cost matrix), timed alone for the record
+    # the HBM-bound member of the same kernel family (materialised dense cost matrix), timed alone for the record
     kd = 1024
     nd = min(n_loc, 1 << 20)
-    od = torch.empty((nd, kd + 1), dtype=torch.int16, device=dev)
-    for _ in range(2):
-        ctx.data_cost_dense(d_pts[:nd], d_hyp[:kd], elem_bytes=2, out=od)
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record()
-    for _ in range(3):
-        ctx.data_cost_dense(d_pts[:nd], d_hyp[:kd], elem_bytes=2, out=od)
-    b.record()
-    torch.cuda.synchronize()
-    dense_ms = a.elapsed_time(b) / 3
-    hbm_peak = None
     try:
-        hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+        hbm_peak, hbm_src = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"], "MEASURED_PEAKS.json hbm_gbs"
     except Exception:
-        hbm_peak = 6650.0
-    dense_gbs = nd * (kd + 1) * 2 / (dense_ms * 1e-3) / 1e9
-    roofline_dense = {"bound": "hbm", "achieved": dense_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": dense_gbs / hbm_peak,
-                      "traffic": None, "kernel": "cost_dense_kernel<int16>",
-                      "note": "materialised N x (K+1) matrix; at 2 B/residual B200's HBM outruns the ~20 FP32-pipe "
-                              "instructions a residual + cost needs, so this member is issue-bound, not HBM-bound",
-                      "algorithmic": f"2 B/residual x {nd} x {kd + 1} per launch", "kernel_ms": dense_ms}
+        hbm_peak, hbm_src = 6650.0, "fallback of B200_PROFILING.md"
+
+    def time_dense(elem_bytes, dtype):
+        od = torch.empty((nd, kd + 1), dtype=dtype, device=dev)
+        for _ in range(2):
+            ctx.data_cost_dense(d_pts[:nd], d_hyp[:kd], elem_bytes=elem_bytes, out=od)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(3):
+            ctx.data_cost_dense(d_pts[:nd], d_hyp[:kd], elem_bytes=elem_bytes, out=od)
+        b.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b) / 3
+        return ms, nd * (kd + 1) * elem_bytes / (ms * 1e-3) / 1e9
+
+    ms32, gbs32 = time_dense(4, torch.int32)
+    ms16, gbs16 = time_dense(2, torch.int16)
+    roofline_dense = {"bound": "hbm", "achieved": gbs32, "peak": hbm_peak, "unit": "GB/s", "frac": gbs32 / hbm_peak,
+                      "traffic": None, "kernel": "cost_dense_tiled_kernel<int32>", "peak_source": hbm_src,
+                      "algorithmic": f"4 B/residual x {nd} x {kd + 1} per launch (the array GCO's setDataCost(int*) indexes)",
+                      "kernel_ms": ms32,
+                      "int16": {"achieved": gbs16, "frac": gbs16 / hbm_peak, "kernel_ms": ms16,
+                                "note": "2 B/residual: the ~12 issue slots a residual + cost needs outrun by HBM, "
+                                        "issue-bound rather than HBM-bound"}}
 
     # ---- CPU baseline (oracle port) on a bounded sample -----------------------------------------------------------------------
     cpu = None

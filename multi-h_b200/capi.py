@@ -27,7 +27,7 @@ SYMBOLS = [
     "mh_hypotheses_to_host", "mh_prefilter", "mh_prefilter_device", "mh_haf_hypotheses", "mh_data_cost_dense", "mh_residuals", "mh_data_cost_fused",
     "mh_inlier_stats", "mh_inliers_of_homography", "mh_features10", "mh_features6", "mh_set_rng_state", "mh_get_rng_state", "mh_meanshift", "mh_refit_haf",
     "mh_refit_haf_accumulate", "mh_refit_haf_solve", "mh_labels_from_best", "mh_pack_inlier_counts", "mh_refit_3pt", "mh_modes_to_hypotheses", "mh_neighbourhood", "mh_alpha_expansion", "mh_process", "mh_get_energy",
-    "mh_get_iterations", "mh_get_stage_ms", "mh_diag_fp32_peak", "mh_diag_mma_tf32_peak", "mh_diag_set_fused_variant", "mh_diag_set_fast_config", "mh_diag_get_fast_config",
+    "mh_get_iterations", "mh_get_stage_ms", "mh_diag_fp32_peak", "mh_diag_mma_tf32_peak", "mh_diag_set_fused_variant", "mh_diag_set_fast_config", "mh_diag_get_fast_config", "mh_diag_set_dense_variant",
 ]
 
 
@@ -400,6 +400,9 @@ class Context:
 
     def set_fast_config(self, v):
         self._check(lib().mh_diag_set_fast_config(self._h, int(v)))
+
+    def set_dense_variant(self, v):
+        self._check(lib().mh_diag_set_dense_variant(self._h, int(v)))
 
     def get_fast_config(self):
         return int(lib().mh_diag_get_fast_config(self._h))
