@@ -225,7 +225,8 @@ mh_status mh_diag_set_fused_variant(mh_ctx* ctx, int32_t variant);
  * 5 = 128x7 (default), 6 = 128x4 — tuning aid. */
 mh_status mh_diag_set_fast_config(mh_ctx* ctx, int32_t config);
 int32_t mh_diag_get_fast_config(mh_ctx* ctx);
-/* 1 = tiled dense-cost kernel with TMA row stores (default), 0 = first-generation scalar-store kernel (A/B evidence) */
+/* 1 = tiled dense-cost kernel with TMA row stores (default; float->int through a denormal product), 2 / 3 = same kernel with
+ * the 2^23-magic / F2I conversion, 0 = first-generation scalar-store kernel (A/B evidence) */
 mh_status mh_diag_set_dense_variant(mh_ctx* ctx, int32_t variant);
 
 #ifdef __cplusplus

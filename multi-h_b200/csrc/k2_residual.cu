@@ -68,14 +68,16 @@ __global__ void __launch_bounds__(DENSE_THREADS) cost_dense_kernel(const float4*
 }
 
 mh_status launch_cost_dense_tiled(mh_ctx* ctx, const float4* d_pts, int64_t N, const float* d_hyp, int K, void* d_cost,
-                                  int elem_bytes);   // k2_dense.cu
-int g_dense_variant = 1;   // 1 = cost_dense_tiled_kernel (TMA row stores, default), 0 = cost_dense_kernel (scalar stores)
+                                  int elem_bytes, int conv);   // k2_dense.cu
+// 1 = cost_dense_tiled_kernel (TMA row stores; float->int through a denormal product, default), 2 / 3 = the same kernel with
+// the 2^23-magic / F2I conversion, 0 = cost_dense_kernel (first generation, scalar stores)
+int g_dense_variant = 1;
 
 mh_status launch_cost_dense(mh_ctx* ctx, const float4* d_pts, int64_t N, const float* d_hyp, int K, void* d_cost,
                             int elem_bytes) {
   if (N <= 0 || K < 0) return MH_OK;
   if (elem_bytes != 2 && elem_bytes != 4) return fail(ctx, MH_EINVAL, "mh_data_cost_dense: elem_bytes must be 2 or 4");
-  if (g_dense_variant == 1) return launch_cost_dense_tiled(ctx, d_pts, N, d_hyp, K, d_cost, elem_bytes);
+  if (g_dense_variant >= 1) return launch_cost_dense_tiled(ctx, d_pts, N, d_hyp, K, d_cost, elem_bytes, g_dense_variant);
   const CostParams cp = cost_params(ctx);
   dim3 grid((unsigned)((N + DENSE_PT - 1) / DENSE_PT), (unsigned)std::max(1, (K + DENSE_THREADS - 1) / DENSE_THREADS));
   if (elem_bytes == 4)

@@ -119,9 +119,10 @@ def _inlier_reference(ctx, d_pts, d_hyp):
 
 
 def test_k2_dense_tiled_equals_scalar_kernel(gpu_ctx, dev, scene, hyps):
-    """The TMA-store dense kernel (default) against the first-generation scalar-store kernel: same bits for every shape —
-    ragged row counts, K + 1 odd/even (every 16-byte phase of a row start), chunk boundaries at 512 columns, K = 0, both
-    element sizes, and an output pointer that is only element-aligned."""
+    """The pipelined TMA-store dense kernel (default) against the first-generation scalar-store kernel: same bits for every
+    shape — ragged row counts, K + 1 odd/even (every 16-byte phase of a row start), chunk boundaries at 512 columns, thin
+    column tails (own kernel) and partial chunks, K = 0, both element sizes, an output pointer that is only element-aligned —
+    and for all three float->int conversions (1 = denormal product, 2 = 2^23 magic, 3 = F2I)."""
     import torch
 
     gpu_ctx.set_geometry(scene.F, scene.pts)
@@ -129,20 +130,22 @@ def test_k2_dense_tiled_equals_scalar_kernel(gpu_ctx, dev, scene, hyps):
     reps = (2100 + d_all.shape[0] - 1) // d_all.shape[0]
     d_big = torch.cat([d_all] * reps)[:2100].contiguous()
     try:
-        for n, k in [(1, 1), (17, 0), (1000, 3), (999, 510), (1001, 511), (1003, 512), (515, 1023), (333, 1024), (77, 2100)]:
+        for n, k in [(1, 1), (17, 0), (1000, 3), (999, 510), (1001, 511), (1003, 512), (640, 128), (50, 639), (260, 700), (515, 1023), (100, 1152),
+                     (4099, 1024), (77, 2100)]:
             pts = dev[0][:n].contiguous()
             hy = d_big[:k].contiguous()
             for eb, dt in ((4, torch.int32), (2, torch.int16)):
                 gpu_ctx.set_dense_variant(0)
                 ref = gpu_ctx.data_cost_dense(pts, hy, elem_bytes=eb)
-                gpu_ctx.set_dense_variant(1)
-                got = gpu_ctx.data_cost_dense(pts, hy, elem_bytes=eb)
-                assert got.shape == (n, k + 1) and torch.equal(got, ref), (n, k, eb)
-                buf = torch.full((n * (k + 1) + 9,), -7, dtype=dt, device="cuda")      # element-aligned, not 16-B-aligned
-                view = buf[3:3 + n * (k + 1)].view(n, k + 1)
-                gpu_ctx.data_cost_dense(pts, hy, elem_bytes=eb, out=view)
-                assert torch.equal(view, ref), (n, k, eb, "offset")
-                assert bool((buf[:3] == -7).all()) and bool((buf[3 + n * (k + 1):] == -7).all())   # nothing outside
+                for variant in (1, 2, 3):
+                    gpu_ctx.set_dense_variant(variant)
+                    got = gpu_ctx.data_cost_dense(pts, hy, elem_bytes=eb)
+                    assert got.shape == (n, k + 1) and torch.equal(got, ref), (n, k, eb, variant)
+                    buf = torch.full((n * (k + 1) + 9,), -7, dtype=dt, device="cuda")   # element-aligned, not 16-B-aligned
+                    view = buf[3:3 + n * (k + 1)].view(n, k + 1)
+                    gpu_ctx.data_cost_dense(pts, hy, elem_bytes=eb, out=view)
+                    assert torch.equal(view, ref), (n, k, eb, variant, "offset")
+                    assert bool((buf[:3] == -7).all()) and bool((buf[3 + n * (k + 1):] == -7).all())   # nothing outside
     finally:
         gpu_ctx.set_dense_variant(1)
 
