@@ -228,6 +228,9 @@ int32_t mh_diag_get_fast_config(mh_ctx* ctx);
 /* 1 = tiled dense-cost kernel with TMA row stores (default; float->int through a denormal product), 2 / 3 = same kernel with
  * the 2^23-magic / F2I conversion, 0 = first-generation scalar-store kernel (A/B evidence) */
 mh_status mh_diag_set_dense_variant(mh_ctx* ctx, int32_t variant);
+/* where the alternating optimisation of the last mh_process spent its time, ms: [0] mean-shift of the hypotheses
+ * [1] mode fit + inlier scan + straightness [2] data-cost matrix (+ D2H) [3] host alpha-expansion [4] refit */
+mh_status mh_diag_get_alternating_ms(const mh_ctx* ctx, double ms[5]);
 
 #ifdef __cplusplus
 }

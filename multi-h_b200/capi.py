@@ -27,7 +27,7 @@ SYMBOLS = [
     "mh_hypotheses_to_host", "mh_prefilter", "mh_prefilter_device", "mh_haf_hypotheses", "mh_data_cost_dense", "mh_residuals", "mh_data_cost_fused",
     "mh_inlier_stats", "mh_inliers_of_homography", "mh_features10", "mh_features6", "mh_set_rng_state", "mh_get_rng_state", "mh_meanshift", "mh_refit_haf",
     "mh_refit_haf_accumulate", "mh_refit_haf_solve", "mh_labels_from_best", "mh_pack_inlier_counts", "mh_refit_3pt", "mh_modes_to_hypotheses", "mh_neighbourhood", "mh_alpha_expansion", "mh_process", "mh_get_energy",
-    "mh_get_iterations", "mh_get_stage_ms", "mh_diag_fp32_peak", "mh_diag_mma_tf32_peak", "mh_diag_set_fused_variant", "mh_diag_set_fast_config", "mh_diag_get_fast_config", "mh_diag_set_dense_variant",
+    "mh_get_iterations", "mh_get_stage_ms", "mh_diag_fp32_peak", "mh_diag_mma_tf32_peak", "mh_diag_set_fused_variant", "mh_diag_set_fast_config", "mh_diag_get_fast_config", "mh_diag_set_dense_variant", "mh_diag_get_alternating_ms",
 ]
 
 
@@ -417,6 +417,11 @@ class Context:
     @property
     def iterations(self):
         return int(lib().mh_get_iterations(self._h))
+
+    def alternating_ms(self):
+        ms = np.zeros(5)
+        self._check(lib().mh_diag_get_alternating_ms(self._h, _p(ms, C.c_double)))
+        return dict(zip(["meanshift", "mode_fit_inlier_scan", "data_cost", "graph_cut", "refit"], ms.tolist()))
 
     def stage_ms(self):
         ms = np.zeros(5)

@@ -546,5 +546,10 @@ mh_status mh_get_stage_ms(const mh_ctx* ctx, double ms[5]) {
   for (int i = 0; i < 5; ++i) ms[i] = ctx->stage_ms[i];
   return MH_OK;
 }
+mh_status mh_diag_get_alternating_ms(const mh_ctx* ctx, double ms[5]) {
+  if (!ctx || !ms) return MH_EINVAL;
+  for (int i = 0; i < 5; ++i) ms[i] = ctx->alt_ms[i];
+  return MH_OK;
+}
 
 }  // extern "C"

@@ -63,6 +63,7 @@ struct mh_ctx {
   double energy = 0.0;
   int32_t iterations = 0;
   double stage_ms[5] = {0, 0, 0, 0, 0};
+  double alt_ms[5] = {0, 0, 0, 0, 0};   // inside the alternating optimisation: mean-shift, mode fit + inlier scan, data cost, graph cut, refit
 };
 
 namespace mh {

@@ -201,10 +201,13 @@ mh_status mh_process(mh_ctx* ctx, const double* pts, const double* aff, const do
   int not_changed_number = 0, iteration_number = 0;
   ctx->energy = 0.0;
   const int potts = (int)std::round(100.0 * P.lambda);  // smoothnessEnergy, MultiH.cpp:506-511
+  for (double& v : ctx->alt_ms) v = 0.0;
+  double tm = 0.0;
   while (iteration_number++ < P.max_iterations) {
     bool changed = false;
     // -- MergingStep (MultiH.cpp:352-471)
     if (K > 0) {
+      tm = now_ms();
       MH_TRY(upload_hyps(K));
       MH_TRY(b_feat6.alloc(ctx, sizeof(double) * 6 * (uint64_t)K));
       MH_TRY(launch_features6(ctx, b_hyp.as<float>(), K, b_feat6.as<double>(), precise ? b_hyp64.as<double>() : nullptr));
@@ -212,6 +215,8 @@ mh_status mh_process(mh_ctx* ctx, const double* pts, const double* aff, const do
       MH_TRY(b_assign.alloc(ctx, sizeof(int32_t) * (uint64_t)K));
       int32_t Cm = 0;
       MH_TRY(mh_meanshift(ctx, b_feat6.p, K, 6, P.thr_homography, b_centres.p, K, b_assign.p, &Cm, nullptr));
+      ctx->alt_ms[0] += now_ms() - tm;
+      tm = now_ms();
       std::vector<float> merged;
       std::vector<double> merged64;
       int Kn = 0;
@@ -249,6 +254,7 @@ mh_status mh_process(mh_ctx* ctx, const double* pts, const double* aff, const do
       }
       changed = Kn != K;  // MultiH.cpp:468
       if (changed) { hyp.swap(merged); hyp64.swap(merged64); K = Kn; }
+      ctx->alt_ms[1] += now_ms() - tm;
     }
     if (changed) not_changed_number = 0; else ++not_changed_number;
 
@@ -264,6 +270,7 @@ mh_status mh_process(mh_ctx* ctx, const double* pts, const double* aff, const do
 
     // -- LabelingStep (MultiH.cpp:513-602)
     const int L = K + 1;
+    tm = now_ms();
     MH_TRY(upload_hyps(K));
     MH_TRY(b_cost.alloc(ctx, sizeof(int32_t) * (uint64_t)N * L));
     if (precise) MH_TRY(launch_cost_dense64(ctx, pts64, N, b_hyp64.as<double>(), K, b_cost.as<int32_t>()));
@@ -276,8 +283,12 @@ mh_status mh_process(mh_ctx* ctx, const double* pts, const double* aff, const do
       init_ptr = init.data();
     }
     int64_t e64 = 0;
+    ctx->alt_ms[2] += now_ms() - tm;
+    tm = now_ms();
     MH_TRY(mh_alpha_expansion(ctx, cost.data(), N, L, potts, offsets.data(), adj.data(), init_ptr, P.max_gc_cycles,
                               gc_labels.data(), &e64));
+    ctx->alt_ms[3] += now_ms() - tm;
+    tm = now_ms();
     const double energy = (double)e64;
     if (trace) std::fprintf(stderr, "[mh_process] iteration %d: K = %d changed = %d energy = %.0f\n", iteration_number, K, (int)changed, energy);
     for (int i = 0; i < N; ++i) labeling[i] = gc_labels[i] - 1;  // MultiH.cpp:547-568
@@ -286,6 +297,7 @@ mh_status mh_process(mh_ctx* ctx, const double* pts, const double* aff, const do
                             nullptr, pts64, aff64, precise ? b_hyp64.as<double>() : nullptr));  // MultiH.cpp:587-599
     MH_TRY(mh_memcpy_d2h(ctx, hyp.data(), b_hyp.p, sizeof(float) * 12 * (size_t)K));
     if (precise) MH_TRY(mh_memcpy_d2h(ctx, hyp64.data(), b_hyp64.p, sizeof(double) * 9 * (size_t)K));
+    ctx->alt_ms[4] += now_ms() - tm;
 
     if ((!changed && std::fabs(lastEnergy - energy) < P.convergence) || not_changed_number > 10) {  // MultiH.cpp:295
       ctx->energy = energy;
