@@ -51,8 +51,8 @@ class MaxFlow {
     else if (to_sink > from_source) add_edge(x, t_, to_sink - from_source, 0);
   }
   void solve() {
-    std::vector<int> level(n_), it(n_), queue(n_), stack;
-    std::vector<int> path;  // arcs on the current DFS path
+    std::vector<int>&level = level_, &it = it_, &queue = queue_, &path = path_;   // arcs on the current DFS path
+    level.resize(n_); it.resize(n_); queue.resize(n_);
     for (;;) {
       std::fill(level.begin(), level.end(), -1);
       int qh = 0, qt = 0;
@@ -108,7 +108,7 @@ class MaxFlow {
 
  private:
   int n_ = 0, s_ = 0, t_ = 0;
-  std::vector<int> head_, to_, next_;
+  std::vector<int> head_, to_, next_, level_, it_, queue_, path_;
   std::vector<int64_t> cap_;
   std::vector<char> reach_t_;
 };
@@ -166,6 +166,22 @@ static int64_t total_energy(const int32_t* cost, int N, int L, int potts, const 
   return e;
 }
 
+// The neighbourhood is the same for every labelling step of a pair (MultiH.cpp:231-253 builds it once), so the symmetrised
+// graph is kept between calls: one entry per thread, keyed on the content of the caller's CSR.
+struct PreparedGraph {
+  uint64_t key = 0;
+  int N = -1;
+  int64_t nnz = -1;
+  SymGraph g;
+};
+static uint64_t csr_key(int N, const int64_t* offsets, const int32_t* adj) {
+  uint64_t h = 1469598103934665603ull;
+  auto mix = [&](uint64_t v) { h = (h ^ v) * 1099511628211ull; };
+  for (int i = 0; i <= N; ++i) mix((uint64_t)offsets[i]);
+  for (int64_t e = 0; e < offsets[N]; ++e) mix((uint32_t)adj[e]);
+  return h;
+}
+
 mh_status alpha_expansion(const int32_t* cost, int N, int L, int potts, const int64_t* offsets, const int32_t* adj,
                           const int32_t* init, int max_cycles, int32_t* lab, int64_t* energy_out) {
   if (N <= 0 || L < 1) return MH_EINVAL;
@@ -173,10 +189,20 @@ mh_status alpha_expansion(const int32_t* cost, int N, int L, int potts, const in
     lab[i] = init ? init[i] : 0;
     if (lab[i] < 0 || lab[i] >= L) return MH_EINVAL;
   }
-  SymGraph g;
-  static const int64_t zero_off[1] = {0};
-  if (offsets && adj) symmetrise(N, offsets, adj, g);
-  else { g.off.assign(N + 1, 0); (void)zero_off; }
+  static thread_local PreparedGraph prepared;
+  static thread_local SymGraph no_edges;
+  const SymGraph* gp = &no_edges;
+  if (offsets && adj) {
+    const uint64_t key = csr_key(N, offsets, adj);
+    if (prepared.N != N || prepared.nnz != offsets[N] || prepared.key != key) {
+      symmetrise(N, offsets, adj, prepared.g);
+      prepared.N = N; prepared.nnz = offsets[N]; prepared.key = key;
+    }
+    gp = &prepared.g;
+  } else {
+    no_edges.off.assign(N + 1, 0);
+  }
+  const SymGraph& g = *gp;
   const bool have_edges = !g.nbr.empty();
 
   if (!have_edges) {  // GCO solveSpecialCases: data costs only -> per-site argmin, first label wins ties
@@ -190,29 +216,75 @@ mh_status alpha_expansion(const int32_t* cost, int N, int L, int potts, const in
     return MH_OK;
   }
 
-  // W[i] = largest amount the pairwise terms of site i can drop when i switches: a site whose data cost would rise by
-  // MORE than W[i] keeps its label in every minimiser of the move's binary energy, so it is fixed (x = 1) and left out of
-  // the flow network — an exact reduction that shrinks most moves to the few sites near hypothesis alpha.
-  std::vector<int64_t> W(N, 0);
+  // Exact reduction of a move's binary problem.  Let S be the set of sites that may still switch to alpha.  Switching site i
+  // (data cost rises by D_i) lowers its pairwise terms by at most
+  //     W_i(S) = SUM_{j : l_j = alpha or j in S} w_ij  -  SUM_{j fixed, l_j = l_i} w_ij
+  // (a fixed neighbour with another label costs w either way).  If D_i > W_i(S), dropping i from any switch set inside S
+  // strictly lowers the energy, so no minimiser inside S switches i: i is fixed and S shrinks.  Starting from all sites and
+  // iterating to the fixed point leaves the few sites near hypothesis alpha's support — often none, and then the move is a
+  // no-op that needs no flow.  Every minimiser lies inside the final S, so the reduced problem has the same minimisers and
+  // the same maximal one (the labelling GCO returns).
+  std::vector<int64_t> Wall(N, 0);   // SUM_j w_ij
   for (int i = 0; i < N; ++i)
-    for (int64_t k = g.off[i]; k < g.off[i + 1]; ++k) W[i] += (int64_t)potts * g.w[k];
+    for (int64_t k = g.off[i]; k < g.off[i + 1]; ++k) Wall[i] += (int64_t)potts * g.w[k];
 
-  std::vector<int> var(N, -1), cand;
+  std::vector<int> var(N, -1), cand, work;
   std::vector<int32_t> trial(N);
-  std::vector<int64_t> src, snk;
-  MaxFlow mf;
+  std::vector<int64_t> src, snk, Wcur, Dcur;
+  static thread_local MaxFlow mf;
   int64_t E = total_energy(cost, N, L, potts, g, lab);
   if (max_cycles < 0) max_cycles = 1 << 30;
-  for (int cycle = 0; cycle < max_cycles; ++cycle) {
+  int idle_moves = 0;   // consecutive moves that changed nothing: L of them = a full sweep over an unchanged labelling
+  for (int cycle = 0; cycle < max_cycles && idle_moves < L; ++cycle) {
     const int64_t E_old = E;
-    for (int alpha = 0; alpha < L; ++alpha) {
+    for (int alpha = 0; alpha < L && idle_moves < L; ++alpha) {
+      ++idle_moves;
       cand.clear();
       for (int i = 0; i < N; ++i)
-        if (lab[i] != alpha && (int64_t)cost[(size_t)i * L + alpha] - cost[(size_t)i * L + lab[i]] <= W[i]) {
+        if (lab[i] != alpha && (int64_t)cost[(size_t)i * L + alpha] - cost[(size_t)i * L + lab[i]] <= Wall[i]) {
           var[i] = (int)cand.size();
           cand.push_back(i);
         }
+      // fixed point of the reduction: one pass for W_i(S), then a work list — dropping i lowers W_j of its surviving
+      // neighbours by w_ij (i can no longer turn alpha) and by another w_ij if l_j = l_i (i now certainly disagrees with
+      // alpha-j), which may drop them in turn
+      if (!cand.empty()) {
+        Wcur.resize(cand.size());
+        Dcur.resize(cand.size());
+        work.clear();
+        for (size_t a = 0; a < cand.size(); ++a) {
+          const int i = cand[a];
+          int64_t Wi = 0;
+          for (int64_t k = g.off[i]; k < g.off[i + 1]; ++k) {
+            const int j = g.nbr[k];
+            if (lab[j] == alpha || var[j] >= 0) Wi += (int64_t)potts * g.w[k];
+            else if (lab[j] == lab[i]) Wi -= (int64_t)potts * g.w[k];
+          }
+          Wcur[a] = Wi;
+          Dcur[a] = (int64_t)cost[(size_t)i * L + alpha] - cost[(size_t)i * L + lab[i]];
+        }
+        for (size_t a = 0; a < cand.size(); ++a)
+          if (Dcur[a] > Wcur[a]) { work.push_back((int)a); Dcur[a] = INT64_MIN; }   // INT64_MIN marks "queued / dropped"
+        for (size_t q = 0; q < work.size(); ++q) {
+          const int i = cand[work[q]];
+          var[i] = -1;
+          for (int64_t k = g.off[i]; k < g.off[i + 1]; ++k) {
+            const int j = g.nbr[k];
+            const int b2 = var[j];
+            if (b2 < 0 || Dcur[b2] == INT64_MIN) continue;
+            Wcur[b2] -= (int64_t)potts * g.w[k] * (lab[j] == lab[i] ? 2 : 1);
+            if (Dcur[b2] > Wcur[b2]) { work.push_back(b2); Dcur[b2] = INT64_MIN; }
+          }
+        }
+        if (!work.empty()) {
+          size_t keep = 0;
+          for (size_t a = 0; a < cand.size(); ++a)
+            if (Dcur[a] != INT64_MIN) cand[keep++] = cand[a];
+          cand.resize(keep);
+        }
+      }
       if (cand.empty()) continue;
+      for (size_t a = 0; a < cand.size(); ++a) var[cand[a]] = (int)a;
       size_t arcs = 0;
       for (int i : cand) arcs += (size_t)(g.off[i + 1] - g.off[i]);
       mf.reset((int)cand.size(), 2 * arcs + 2 * cand.size());
@@ -265,6 +337,7 @@ mh_status alpha_expansion(const int32_t* cost, int N, int L, int potts, const in
         if (after < before) {
           for (int i : cand) lab[i] = trial[i];
           E += after - before;
+          idle_moves = 0;
         }
       }
       for (int i : cand) var[i] = -1;
