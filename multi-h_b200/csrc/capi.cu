@@ -182,6 +182,8 @@ void mh_destroy(mh_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
   if (ctx->scratch) cudaFree(ctx->scratch);
   if (ctx->staging) cudaFree(ctx->staging);
+  for (void* b : ctx->pbuf)
+    if (b) cudaFree(b);
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;

@@ -59,6 +59,9 @@ struct mh_ctx {
   uint64_t staging_bytes = 0;
   void* pinned = nullptr;
   uint64_t pinned_bytes = 0;
+  // mh_process's working set: grow-only device buffers that live as long as the context (no cudaMalloc in steady state)
+  void* pbuf[24] = {};
+  uint64_t pcap[24] = {};
   // results of the last mh_process
   double energy = 0.0;
   int32_t iterations = 0;

@@ -20,10 +20,18 @@
 // reachability pass from the sink reproduces GCO's moves bit for bit.  Totals
 // are int64 (the reference's EnergyType is a 32-bit int, GCoptimization.h:165-170).
 // ============================================================================
+#include <unistd.h>
+
 #include <algorithm>
+#include <atomic>
 #include <cmath>
+#include <condition_variable>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
+#include <functional>
+#include <mutex>
+#include <thread>
 #include <vector>
 
 #include "../../include/multih_b200.h"
@@ -38,12 +46,12 @@ class MaxFlow {
   void reset(int n_nodes, size_t arc_hint) {
     n_ = n_nodes + 2; s_ = n_nodes; t_ = n_nodes + 1;
     head_.assign(n_, -1);
-    to_.clear(); cap_.clear(); next_.clear();
-    to_.reserve(arc_hint); cap_.reserve(arc_hint); next_.reserve(arc_hint);
+    arc_.clear();
+    arc_.reserve(arc_hint);
   }
   void add_edge(int u, int v, int64_t c_uv, int64_t c_vu) {
-    to_.push_back(v); cap_.push_back(c_uv); next_.push_back(head_[u]); head_[u] = (int)to_.size() - 1;
-    to_.push_back(u); cap_.push_back(c_vu); next_.push_back(head_[v]); head_[v] = (int)to_.size() - 1;
+    arc_.push_back({c_uv, v, head_[u]}); head_[u] = (int)arc_.size() - 1;
+    arc_.push_back({c_vu, u, head_[v]}); head_[v] = (int)arc_.size() - 1;
   }
   // terminal capacities: only the difference needs an arc
   void add_terminal(int x, int64_t from_source, int64_t to_sink) {
@@ -53,14 +61,15 @@ class MaxFlow {
   void solve() {
     std::vector<int>&level = level_, &it = it_, &queue = queue_, &path = path_;   // arcs on the current DFS path
     level.resize(n_); it.resize(n_); queue.resize(n_);
+    Arc* const arc = arc_.data();
     for (;;) {
       std::fill(level.begin(), level.end(), -1);
       int qh = 0, qt = 0;
       queue[qt++] = s_; level[s_] = 0;
-      while (qh < qt) {
+      while (qh < qt && level[t_] < 0) {   // nodes beyond the sink's level cannot lie on a shortest augmenting path
         const int u = queue[qh++];
-        for (int e = head_[u]; e >= 0; e = next_[e])
-          if (cap_[e] > 0 && level[to_[e]] < 0) { level[to_[e]] = level[u] + 1; queue[qt++] = to_[e]; }
+        for (int e = head_[u]; e >= 0; e = arc[e].next)
+          if (arc[e].cap > 0 && level[arc[e].to] < 0) { level[arc[e].to] = level[u] + 1; queue[qt++] = arc[e].to; }
       }
       if (level[t_] < 0) break;
       for (int i = 0; i < n_; ++i) it[i] = head_[i];
@@ -70,24 +79,24 @@ class MaxFlow {
       for (;;) {
         if (u == t_) {
           int64_t f = INT64_MAX;
-          for (int e : path) f = std::min(f, cap_[e]);
-          for (int e : path) { cap_[e] -= f; cap_[e ^ 1] += f; }
+          for (int e : path) f = std::min(f, arc[e].cap);
+          for (int e : path) { arc[e].cap -= f; arc[e ^ 1].cap += f; }
           // restart from the first saturated arc
           size_t k = 0;
-          while (k < path.size() && cap_[path[k]] > 0) ++k;
+          while (k < path.size() && arc[path[k]].cap > 0) ++k;
           path.resize(k);
-          u = path.empty() ? s_ : to_[path.back()];
+          u = path.empty() ? s_ : arc[path.back()].to;
           continue;
         }
         int& e = it[u];
-        while (e >= 0 && !(cap_[e] > 0 && level[to_[e]] == level[u] + 1)) e = next_[e];
-        if (e >= 0) { path.push_back(e); u = to_[e]; }
+        while (e >= 0 && !(arc[e].cap > 0 && level[arc[e].to] == level[u] + 1)) e = arc[e].next;
+        if (e >= 0) { path.push_back(e); u = arc[e].to; }
         else {
           level[u] = -1;  // dead end
           if (path.empty()) break;
           const int back = path.back();
           path.pop_back();
-          u = to_[back ^ 1];
+          u = arc[back ^ 1].to;
         }
       }
     }
@@ -98,18 +107,19 @@ class MaxFlow {
     st[top++] = t_; reach_t_[t_] = 1;
     while (top) {
       const int v = st[--top];
-      for (int e = head_[v]; e >= 0; e = next_[e]) {
-        const int u = to_[e];  // arc v->u is e, arc u->v is e^1
-        if (!reach_t_[u] && cap_[e ^ 1] > 0) { reach_t_[u] = 1; st[top++] = u; }
+      for (int e = head_[v]; e >= 0; e = arc[e].next) {
+        const int u = arc[e].to;  // arc v->u is e, arc u->v is e^1
+        if (!reach_t_[u] && arc[e ^ 1].cap > 0) { reach_t_[u] = 1; st[top++] = u; }
       }
     }
   }
   bool sink_side(int x) const { return reach_t_[x] != 0; }
 
  private:
+  struct Arc { int64_t cap; int to, next; };
   int n_ = 0, s_ = 0, t_ = 0;
-  std::vector<int> head_, to_, next_, level_, it_, queue_, path_;
-  std::vector<int64_t> cap_;
+  std::vector<int> head_, level_, it_, queue_, path_;
+  std::vector<Arc> arc_;
   std::vector<char> reach_t_;
 };
 
@@ -166,6 +176,258 @@ static int64_t total_energy(const int32_t* cost, int N, int L, int potts, const 
   return e;
 }
 
+// ---------------------------------------------------------------------------
+// One expansion move, evaluated on a read-only labelling: which sites would switch to alpha, and by how much the energy
+// would drop.  Everything it reads — labels of the initial candidates C0 (sites whose data cost alone does not forbid
+// alpha) and of their neighbours — is recorded in `touched`, so a caller that evaluated the move on an older labelling
+// can tell whether the result still holds.
+// ---------------------------------------------------------------------------
+struct MoveWS {   // per-thread scratch
+  std::vector<int> var, cand, work;
+  std::vector<int32_t> trial;
+  std::vector<int64_t> src, snk, Wcur, Dcur;
+  MaxFlow mf;
+  void prepare(int N) { if ((int)var.size() != N) { var.assign(N, -1); trial.assign(N, 0); } }
+};
+struct MoveResult {
+  int alpha = -1;
+  int64_t delta = 0;               // energy change if applied (< 0, or 0 with an empty switch list)
+  std::vector<int> sw;             // sites that switch to alpha
+  std::vector<uint64_t> touched;   // bitset over sites: C0 and its neighbours (filled only on request)
+  bool any_c0 = false;
+};
+struct MoveProblem {
+  const int32_t* cost; int N, L, potts;
+  const SymGraph* g;
+  const int64_t* Wall;             // SUM_j w_ij
+};
+
+static void eval_move(const MoveProblem& P, const int32_t* lab, int alpha, MoveWS& ws, MoveResult& r, bool want_touched) {
+  const int N = P.N, L = P.L, potts = P.potts;
+  const int32_t* cost = P.cost;
+  const SymGraph& g = *P.g;
+  std::vector<int>&var = ws.var, &cand = ws.cand, &work = ws.work;
+  std::vector<int64_t>&src = ws.src, &snk = ws.snk, &Wcur = ws.Wcur, &Dcur = ws.Dcur;
+  r.alpha = alpha; r.delta = 0; r.sw.clear(); r.any_c0 = false;
+  if (want_touched) r.touched.assign(((size_t)N + 63) / 64, 0);
+  // Exact reduction of the move's binary problem.  Let S be the set of sites that may still switch to alpha.  Switching
+  // site i (data cost rises by D_i) lowers its pairwise terms by at most
+  //     W_i(S) = SUM_{j : l_j = alpha or j in S} w_ij  -  SUM_{j fixed, l_j = l_i} w_ij
+  // (a fixed neighbour with another label costs w either way).  If D_i > W_i(S), dropping i from any switch set inside S
+  // strictly lowers the energy, so no minimiser inside S switches i: i is fixed and S shrinks.  Starting from all sites
+  // and iterating to the fixed point leaves the few sites near hypothesis alpha's support — often none, and then the move
+  // is a no-op that needs no flow.  Every minimiser lies inside the final S, so the reduced problem has the same
+  // minimisers and the same maximal one (the labelling GCO returns).
+  cand.clear();
+  for (int i = 0; i < N; ++i)
+    if (lab[i] != alpha && (int64_t)cost[(size_t)i * L + alpha] - cost[(size_t)i * L + lab[i]] <= P.Wall[i]) {
+      var[i] = (int)cand.size();
+      cand.push_back(i);
+    }
+  if (cand.empty()) return;
+  r.any_c0 = true;
+  // one pass for W_i(S), then a work list — dropping i lowers W_j of its surviving neighbours by w_ij (i can no longer turn
+  // alpha) and by another w_ij if l_j = l_i (i now certainly disagrees with alpha-j), which may drop them in turn
+  Wcur.resize(cand.size());
+  Dcur.resize(cand.size());
+  work.clear();
+  for (size_t a = 0; a < cand.size(); ++a) {
+    const int i = cand[a];
+    int64_t Wi = 0;
+    if (want_touched) {
+      r.touched[(size_t)i >> 6] |= 1ull << (i & 63);
+      for (int64_t k = g.off[i]; k < g.off[i + 1]; ++k) r.touched[(size_t)g.nbr[k] >> 6] |= 1ull << (g.nbr[k] & 63);
+    }
+    const int li = lab[i];
+    int32_t wsum = 0;   // branch-free: the tests are data-dependent coin flips
+    for (int64_t k = g.off[i]; k < g.off[i + 1]; ++k) {
+      const int j = g.nbr[k];
+      const int lj = lab[j];
+      const int may = (lj == alpha) | (var[j] >= 0);
+      wsum += g.w[k] * (may - ((may ^ 1) & (lj == li)));
+    }
+    Wi = (int64_t)potts * wsum;
+    Wcur[a] = Wi;
+    Dcur[a] = (int64_t)cost[(size_t)i * L + alpha] - cost[(size_t)i * L + lab[i]];
+  }
+  for (size_t a = 0; a < cand.size(); ++a)
+    if (Dcur[a] > Wcur[a]) { work.push_back((int)a); Dcur[a] = INT64_MIN; }   // INT64_MIN marks "queued / dropped"
+  for (size_t q = 0; q < work.size(); ++q) {
+    const int i = cand[work[q]];
+    var[i] = -1;
+    for (int64_t k = g.off[i]; k < g.off[i + 1]; ++k) {
+      const int j = g.nbr[k];
+      const int b2 = var[j];
+      if (b2 < 0 || Dcur[b2] == INT64_MIN) continue;
+      Wcur[b2] -= (int64_t)potts * g.w[k] * (lab[j] == lab[i] ? 2 : 1);
+      if (Dcur[b2] > Wcur[b2]) { work.push_back(b2); Dcur[b2] = INT64_MIN; }
+    }
+  }
+  if (!work.empty()) {
+    size_t keep = 0;
+    for (size_t a = 0; a < cand.size(); ++a)
+      if (Dcur[a] != INT64_MIN) cand[keep++] = cand[a];
+    cand.resize(keep);
+  }
+  if (cand.empty()) return;
+  for (size_t a = 0; a < cand.size(); ++a) var[cand[a]] = (int)a;
+  size_t arcs = 0;
+  for (int i : cand) arcs += (size_t)(g.off[i + 1] - g.off[i]);
+  MaxFlow& mf = ws.mf;
+  mf.reset((int)cand.size(), 2 * arcs + 2 * cand.size());
+  src.assign(cand.size(), 0);
+  snk.assign(cand.size(), 0);
+  int64_t before = 0;   // energy of the terms below under the current labelling = SUM of the source-arc payments
+  for (size_t a = 0; a < cand.size(); ++a) {
+    const int i = cand[a], li = lab[i];
+    // x = 0 (source side) takes alpha and pays E0 on the arc to the sink; x = 1 keeps its label.  Per neighbour j:
+    //   l_j = alpha            : pay w iff i keeps its label                                  -> source arc += w
+    //   j fixed (l_j != alpha) : alpha pays w, keeping pays w [l_i != l_j]                     -> sink += w, source += w [..]
+    //   j in the network, j < i: E00 = 0, E01 = E10 = w, E11 = w [l_i != l_j]: pay E11 on i's source arc, remaining
+    //                            table [0, w; w - E11, 0] becomes the arc pair
+    // (sums kept branch-free; only the arc insertion branches)
+    int32_t s_w = 0, t_w = 0;
+    for (int64_t k = g.off[i]; k < g.off[i + 1]; ++k) {
+      const int j = g.nbr[k], lj = lab[j], vj = var[j], w = g.w[k];
+      const int isA = lj == alpha, inS = vj >= 0, diff = li != lj;
+      const int fixed = (isA | inS) ^ 1, both = inS & (j < i);
+      s_w += w * (isA | (diff & (fixed | both)));
+      t_w += w * fixed;
+      if (both) mf.add_edge((int)a, vj, (int64_t)potts * w, (int64_t)potts * w * (diff ^ 1));
+    }
+    snk[a] = cost[(size_t)i * L + alpha] + (int64_t)potts * t_w;
+    src[a] = cost[(size_t)i * L + li] + (int64_t)potts * s_w;
+    before += src[a];
+  }
+  for (size_t a = 0; a < cand.size(); ++a) mf.add_terminal((int)a, src[a], snk[a]);
+  mf.solve();
+  bool any = false;
+  std::vector<int32_t>& trial = ws.trial;
+  for (size_t a = 0; a < cand.size(); ++a) {
+    const bool sw = !mf.sink_side((int)a);
+    trial[cand[a]] = sw ? alpha : lab[cand[a]];
+    any |= sw;
+  }
+  if (any) {
+    // energy of the same terms under the trial labelling (trial = lab outside the network)
+    int64_t after = 0;
+    for (size_t a = 0; a < cand.size(); ++a) {
+      const int i = cand[a], ti = trial[i];
+      after += cost[(size_t)i * L + ti];
+      int32_t cut = 0;
+      for (int64_t k = g.off[i]; k < g.off[i + 1]; ++k) {
+        const int j = g.nbr[k], vj = var[j];
+        const int lj = vj >= 0 ? trial[j] : lab[j];
+        cut += g.w[k] * (((vj < 0) | (j < i)) & (ti != lj));
+      }
+      after += (int64_t)potts * cut;
+    }
+    if (after < before) {   // GCO accepts a move only if it strictly lowers the energy
+      r.delta = after - before;
+      for (int i : cand)
+        if (trial[i] == alpha) r.sw.push_back(i);
+    }
+  }
+  for (int i : cand) var[i] = -1;
+}
+
+// ---------------------------------------------------------------------------
+// Worker threads for speculative move evaluation (below).  One pool per process, created on first use and re-created
+// after a fork; a caller that finds it busy (another host thread is inside mh_alpha_expansion) simply runs sequentially.
+// Workers sleep between sessions and spin inside one (a move takes ~50 us: a futex round trip per move would eat it).
+// ---------------------------------------------------------------------------
+class MovePool {
+ public:
+  static MovePool* acquire() {   // nullptr: no threads wanted / pool busy
+    static std::mutex gm;
+    static MovePool* pool = nullptr;
+    static pid_t owner = 0;
+    std::lock_guard<std::mutex> lk(gm);
+    int want = (int)std::thread::hardware_concurrency();
+    if (const char* e = std::getenv("MH_GC_THREADS")) want = std::atoi(e);
+    want = std::min(want, 8);   // measured on the 16-core B200 host: 8 -> 16 threads gains 2 %
+    if (want < 2) return nullptr;
+    if (!pool || owner != getpid()) { pool = new MovePool(want - 1); owner = getpid(); }   // (a forked child leaks the parent's)
+    if (pool->busy_) return nullptr;
+    pool->busy_ = true;
+    pool->begin_session();
+    return pool;
+  }
+  void release() {
+    end_session();
+    busy_ = false;   // only the owner of busy_ writes it back; acquire() reads it under the global mutex
+  }
+  int threads() const { return (int)th_.size() + 1; }
+  // fn(job, thread) for job in [0, n): the caller takes part as thread 0
+  template <typename F> void run(int n, F&& fn) {
+    fn_ = [&](int j, int t) { fn(j, t); };
+    njobs_ = n;
+    done_.store(0, std::memory_order_relaxed);
+    next_.store(0, std::memory_order_relaxed);
+    epoch_.fetch_add(1, std::memory_order_release);
+    work(0);
+    while (done_.load(std::memory_order_acquire) < n) cpu_relax();
+  }
+
+ private:
+  explicit MovePool(int workers) {
+    for (int i = 0; i < workers; ++i) th_.emplace_back([this, i] { loop(i + 1); });
+  }
+  static void cpu_relax() {
+#if defined(__x86_64__) || defined(__i386__)
+    __builtin_ia32_pause();
+#else
+    std::this_thread::yield();
+#endif
+  }
+  void work(int t) {
+    for (;;) {
+      const int j = next_.fetch_add(1, std::memory_order_relaxed);
+      if (j >= njobs_) break;
+      fn_(j, t);
+      done_.fetch_add(1, std::memory_order_release);
+    }
+  }
+  void begin_session() {
+    { std::lock_guard<std::mutex> lk(m_); session_ = true; }
+    cv_.notify_all();
+  }
+  void end_session() {
+    { std::lock_guard<std::mutex> lk(m_); session_ = false; }
+    epoch_.fetch_add(1, std::memory_order_release);   // spinners re-check the session flag
+  }
+  void loop(int t) {
+    uint64_t seen = epoch_.load(std::memory_order_acquire);
+    for (;;) {
+      {
+        std::unique_lock<std::mutex> lk(m_);
+        cv_.wait(lk, [this] { return session_; });
+      }
+      for (;;) {   // inside a session: spin on the epoch
+        const uint64_t e = epoch_.load(std::memory_order_acquire);
+        if (e != seen) {
+          seen = e;
+          bool in_session;
+          { std::lock_guard<std::mutex> lk(m_); in_session = session_; }
+          if (!in_session) break;
+          work(t);
+        } else {
+          cpu_relax();
+        }
+      }
+    }
+  }
+  std::vector<std::thread> th_;
+  std::mutex m_;
+  std::condition_variable cv_;
+  bool session_ = false;
+  bool busy_ = false;
+  std::function<void(int, int)> fn_;
+  int njobs_ = 0;
+  std::atomic<int> next_{0}, done_{0};
+  std::atomic<uint64_t> epoch_{0};
+};
+
 // The neighbourhood is the same for every labelling step of a pair (MultiH.cpp:231-253 builds it once), so the symmetrised
 // graph is kept between calls: one entry per thread, keyed on the content of the caller's CSR.
 struct PreparedGraph {
@@ -173,6 +435,7 @@ struct PreparedGraph {
   int N = -1;
   int64_t nnz = -1;
   SymGraph g;
+  std::vector<int64_t> Wall;
 };
 static uint64_t csr_key(int N, const int64_t* offsets, const int32_t* adj) {
   uint64_t h = 1469598103934665603ull;
@@ -182,6 +445,13 @@ static uint64_t csr_key(int N, const int64_t* offsets, const int32_t* adj) {
   return h;
 }
 
+// GCO's expansion(): sweep the labels 0..L-1 in order, apply a move iff it strictly lowers the energy, stop when a full sweep
+// changes nothing.  The sweep is sequential by definition (move alpha+1 sees the result of move alpha), but a move reads only
+// the labels of its candidate set and their neighbours, and moves of different hypotheses mostly live in different parts of the
+// image.  So a window of upcoming moves is evaluated SPECULATIVELY in parallel on the current labelling, and the results are
+// committed in label order: a result is used iff no site that changed in the meantime belongs to what the move read (its
+// `touched` set) or newly qualifies as a candidate; otherwise the move is evaluated again on the current labelling.  The
+// sequence of applied moves — hence labels and energy — is exactly the sequential one.
 mh_status alpha_expansion(const int32_t* cost, int N, int L, int potts, const int64_t* offsets, const int32_t* adj,
                           const int32_t* init, int max_cycles, int32_t* lab, int64_t* energy_out) {
   if (N <= 0 || L < 1) return MH_EINVAL;
@@ -197,6 +467,9 @@ mh_status alpha_expansion(const int32_t* cost, int N, int L, int potts, const in
     if (prepared.N != N || prepared.nnz != offsets[N] || prepared.key != key) {
       symmetrise(N, offsets, adj, prepared.g);
       prepared.N = N; prepared.nnz = offsets[N]; prepared.key = key;
+      prepared.Wall.assign(N, 0);   // SUM_j w_ij (times potts below: potts may differ between calls)
+      for (int i = 0; i < N; ++i)
+        for (int64_t k = prepared.g.off[i]; k < prepared.g.off[i + 1]; ++k) prepared.Wall[i] += prepared.g.w[k];
     }
     gp = &prepared.g;
   } else {
@@ -216,134 +489,60 @@ mh_status alpha_expansion(const int32_t* cost, int N, int L, int potts, const in
     return MH_OK;
   }
 
-  // Exact reduction of a move's binary problem.  Let S be the set of sites that may still switch to alpha.  Switching site i
-  // (data cost rises by D_i) lowers its pairwise terms by at most
-  //     W_i(S) = SUM_{j : l_j = alpha or j in S} w_ij  -  SUM_{j fixed, l_j = l_i} w_ij
-  // (a fixed neighbour with another label costs w either way).  If D_i > W_i(S), dropping i from any switch set inside S
-  // strictly lowers the energy, so no minimiser inside S switches i: i is fixed and S shrinks.  Starting from all sites and
-  // iterating to the fixed point leaves the few sites near hypothesis alpha's support — often none, and then the move is a
-  // no-op that needs no flow.  Every minimiser lies inside the final S, so the reduced problem has the same minimisers and
-  // the same maximal one (the labelling GCO returns).
-  std::vector<int64_t> Wall(N, 0);   // SUM_j w_ij
-  for (int i = 0; i < N; ++i)
-    for (int64_t k = g.off[i]; k < g.off[i + 1]; ++k) Wall[i] += (int64_t)potts * g.w[k];
+  std::vector<int64_t> Wall(N);
+  for (int i = 0; i < N; ++i) Wall[i] = (int64_t)potts * prepared.Wall[i];
+  const MoveProblem P{cost, N, L, potts, &g, Wall.data()};
 
-  std::vector<int> var(N, -1), cand, work;
-  std::vector<int32_t> trial(N);
-  std::vector<int64_t> src, snk, Wcur, Dcur;
-  static thread_local MaxFlow mf;
-  int64_t E = total_energy(cost, N, L, potts, g, lab);
+  MovePool* pool = (L >= 4 && (int64_t)N * L >= 4096) ? MovePool::acquire() : nullptr;
+  const int nthreads = pool ? pool->threads() : 1;
+  static thread_local std::vector<MoveWS> ws;
+  static thread_local std::vector<MoveResult> res;
+  if ((int)ws.size() < nthreads) ws.resize(nthreads);
+  for (int t = 0; t < nthreads; ++t) ws[t].prepare(N);
+  const int window = pool ? std::min(L, 2 * nthreads) : 1;
+  if ((int)res.size() < window) res.resize(window);
+  MoveWS* const wsp = ws.data();          // (thread_local objects: workers must go through the caller's pointers)
+  MoveResult* const resp = res.data();
+
+  std::vector<int> changed;   // sites committed since the window's snapshot
   if (max_cycles < 0) max_cycles = 1 << 30;
+  const int64_t max_moves = (int64_t)std::min<int64_t>(max_cycles, (1LL << 40) / L) * L;
   int idle_moves = 0;   // consecutive moves that changed nothing: L of them = a full sweep over an unchanged labelling
-  for (int cycle = 0; cycle < max_cycles && idle_moves < L; ++cycle) {
-    const int64_t E_old = E;
-    for (int alpha = 0; alpha < L && idle_moves < L; ++alpha) {
+  int64_t E_cycle = 0, E_delta = 0;   // energy change within the current cycle (GCO stops after a cycle without change)
+  (void)E_cycle;
+  int64_t move = 0;
+  bool stop = false;
+  while (!stop && move < max_moves && idle_moves < L) {
+    const int nw = (int)std::min<int64_t>(window, max_moves - move);
+    const int a0 = (int)(move % L);
+    if (pool && nw > 1)
+      pool->run(nw, [&, wsp, resp](int j, int t) { eval_move(P, lab, (a0 + j) % L, wsp[t], resp[j], true); });
+    changed.clear();
+    for (int j = 0; j < nw && !stop; ++j, ++move) {
+      const int alpha = (a0 + j) % L;
+      bool valid = pool && nw > 1;
+      if (valid && !changed.empty()) {
+        const MoveResult& r = res[j];
+        for (int d : changed) {
+          if (r.any_c0 && ((r.touched[(size_t)d >> 6] >> (d & 63)) & 1ull)) { valid = false; break; }
+          if (lab[d] != alpha && (int64_t)cost[(size_t)d * L + alpha] - cost[(size_t)d * L + lab[d]] <= Wall[d]) { valid = false; break; }
+        }
+      }
+      if (!valid) eval_move(P, lab, alpha, ws[0], res[j], false);
       ++idle_moves;
-      cand.clear();
-      for (int i = 0; i < N; ++i)
-        if (lab[i] != alpha && (int64_t)cost[(size_t)i * L + alpha] - cost[(size_t)i * L + lab[i]] <= Wall[i]) {
-          var[i] = (int)cand.size();
-          cand.push_back(i);
-        }
-      // fixed point of the reduction: one pass for W_i(S), then a work list — dropping i lowers W_j of its surviving
-      // neighbours by w_ij (i can no longer turn alpha) and by another w_ij if l_j = l_i (i now certainly disagrees with
-      // alpha-j), which may drop them in turn
-      if (!cand.empty()) {
-        Wcur.resize(cand.size());
-        Dcur.resize(cand.size());
-        work.clear();
-        for (size_t a = 0; a < cand.size(); ++a) {
-          const int i = cand[a];
-          int64_t Wi = 0;
-          for (int64_t k = g.off[i]; k < g.off[i + 1]; ++k) {
-            const int j = g.nbr[k];
-            if (lab[j] == alpha || var[j] >= 0) Wi += (int64_t)potts * g.w[k];
-            else if (lab[j] == lab[i]) Wi -= (int64_t)potts * g.w[k];
-          }
-          Wcur[a] = Wi;
-          Dcur[a] = (int64_t)cost[(size_t)i * L + alpha] - cost[(size_t)i * L + lab[i]];
-        }
-        for (size_t a = 0; a < cand.size(); ++a)
-          if (Dcur[a] > Wcur[a]) { work.push_back((int)a); Dcur[a] = INT64_MIN; }   // INT64_MIN marks "queued / dropped"
-        for (size_t q = 0; q < work.size(); ++q) {
-          const int i = cand[work[q]];
-          var[i] = -1;
-          for (int64_t k = g.off[i]; k < g.off[i + 1]; ++k) {
-            const int j = g.nbr[k];
-            const int b2 = var[j];
-            if (b2 < 0 || Dcur[b2] == INT64_MIN) continue;
-            Wcur[b2] -= (int64_t)potts * g.w[k] * (lab[j] == lab[i] ? 2 : 1);
-            if (Dcur[b2] > Wcur[b2]) { work.push_back(b2); Dcur[b2] = INT64_MIN; }
-          }
-        }
-        if (!work.empty()) {
-          size_t keep = 0;
-          for (size_t a = 0; a < cand.size(); ++a)
-            if (Dcur[a] != INT64_MIN) cand[keep++] = cand[a];
-          cand.resize(keep);
-        }
+      if (!res[j].sw.empty()) {
+        for (int i : res[j].sw) { lab[i] = alpha; changed.push_back(i); }
+        E_delta += res[j].delta;
+        idle_moves = 0;
       }
-      if (cand.empty()) continue;
-      for (size_t a = 0; a < cand.size(); ++a) var[cand[a]] = (int)a;
-      size_t arcs = 0;
-      for (int i : cand) arcs += (size_t)(g.off[i + 1] - g.off[i]);
-      mf.reset((int)cand.size(), 2 * arcs + 2 * cand.size());
-      src.assign(cand.size(), 0);
-      snk.assign(cand.size(), 0);
-      int64_t before = 0;
-      for (size_t a = 0; a < cand.size(); ++a) {
-        const int i = cand[a];
-        // x = 0 (source side) takes alpha and pays E0 on the arc to the sink; x = 1 keeps its label
-        snk[a] += cost[(size_t)i * L + alpha];
-        src[a] += cost[(size_t)i * L + lab[i]];
-        before += cost[(size_t)i * L + lab[i]];
-        for (int64_t k = g.off[i]; k < g.off[i + 1]; ++k) {
-          const int j = g.nbr[k];
-          const int64_t w = (int64_t)potts * g.w[k];
-          if (lab[j] == alpha) {        // neighbour already alpha: pay w iff i keeps its label
-            src[a] += w; before += w;
-          } else if (var[j] < 0) {      // neighbour keeps l_j != alpha for sure: alpha pays w, keeping pays w*[l_i != l_j]
-            const int64_t e1 = lab[i] != lab[j] ? w : 0;
-            snk[a] += w; src[a] += e1; before += e1;
-          } else if (j < i) {           // both in the network: E00 = 0, E01 = w, E10 = w, E11 = w*[l_i != l_j]
-            const int b2 = var[j];
-            const int64_t e11 = lab[i] != lab[j] ? w : 0;
-            before += e11;
-            src[a] += e11;               // pay e11 on i's source arc, remaining table [0, w; w - e11, 0]
-            mf.add_edge((int)a, b2, w, w - e11);
-          }
-        }
+      if (alpha == L - 1) {   // end of a cycle: GCO stops when the cycle left the energy unchanged
+        if (E_delta == 0) stop = true;
+        E_delta = 0;
       }
-      for (size_t a = 0; a < cand.size(); ++a) mf.add_terminal((int)a, src[a], snk[a]);
-      mf.solve();
-      bool any = false;
-      for (size_t a = 0; a < cand.size(); ++a) {
-        const bool sw = !mf.sink_side((int)a);
-        trial[cand[a]] = sw ? alpha : lab[cand[a]];
-        any |= sw;
-      }
-      if (any) {
-        // energy of the same terms under the trial labelling
-        int64_t after = 0;
-        for (size_t a = 0; a < cand.size(); ++a) {
-          const int i = cand[a];
-          after += cost[(size_t)i * L + trial[i]];
-          for (int64_t k = g.off[i]; k < g.off[i + 1]; ++k) {
-            const int j = g.nbr[k];
-            const int lj = var[j] >= 0 ? trial[j] : lab[j];
-            if ((var[j] < 0 || j < i) && trial[i] != lj) after += (int64_t)potts * g.w[k];
-          }
-        }
-        if (after < before) {
-          for (int i : cand) lab[i] = trial[i];
-          E += after - before;
-          idle_moves = 0;
-        }
-      }
-      for (int i : cand) var[i] = -1;
+      if (idle_moves >= L) stop = true;
     }
-    if (E == E_old) break;
   }
+  if (pool) pool->release();
   if (energy_out) *energy_out = total_energy(cost, N, L, potts, g, lab);
   return MH_OK;
 }

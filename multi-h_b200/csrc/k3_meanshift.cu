@@ -91,8 +91,16 @@ __device__ __forceinline__ void publish_unvisited(const MsState& st, int lo, int
   }
 }
 
+// SINGLE: the whole problem fits one CTA's stride loop (N <= MS_SINGLE_MAX: the bundled pairs' 1-2k correspondences, and
+// every merging step's K hypotheses) — a plain launch whose "grid barrier" is __syncthreads(): ~1 us per window iteration
+// instead of ~5 us, which is what the latency-bound small cases pay for.
+constexpr int MS_SINGLE_MAX = 4096;
+template <bool SINGLE>
 __global__ void __launch_bounds__(MS_THREADS) meanshift_kernel(MsState st) {
-  cg::grid_group grid = cg::this_grid();
+  auto grid_sync = [] {
+    if constexpr (SINGLE) __syncthreads();
+    else cg::this_grid().sync();
+  };
   __shared__ double s_mean[MS_MAXD];
   __shared__ double s_red[MS_THREADS / 32][MS_MAXD + 1];
   __shared__ double s_new[MS_MAXD + 1];
@@ -110,7 +118,7 @@ __global__ void __launch_bounds__(MS_THREADS) meanshift_kernel(MsState st) {
   int overflow = 0;
 
   publish_unvisited(st, lo, hi, b, s_int);
-  grid.sync();
+  grid_sync();
   for (;;) {
     // ---- every CTA derives the same seed rank (MS.h:54-56) -------------------------
     int remaining = 0;
@@ -151,7 +159,7 @@ __global__ void __launch_bounds__(MS_THREADS) meanshift_kernel(MsState st) {
       if (tid < D) st.seed_mean[tid] = st.dataT[(size_t)tid * Npad + seed];
     }
     for (int i = lo + tid; i < hi; i += MS_THREADS) st.tvotes[i] = 0;
-    grid.sync();
+    grid_sync();
     if (tid < D) s_mean[tid] = st.seed_mean[tid];
     __syncthreads();
     ++traj;
@@ -195,7 +203,7 @@ __global__ void __launch_bounds__(MS_THREADS) meanshift_kernel(MsState st) {
         for (int w = 0; w < MS_THREADS / 32; ++w) v += s_red[w][tid];
         st.partial[((size_t)par * nb + b) * (MS_MAXD + 1) + tid] = v;
       }
-      grid.sync();
+      grid_sync();
       // every CTA sums the per-CTA partials in the same order -> identical new mean everywhere
       if (warp == 0) {
         for (int j = 0; j <= MS_MAXD; ++j) {
@@ -261,7 +269,7 @@ __global__ void __launch_bounds__(MS_THREADS) meanshift_kernel(MsState st) {
     // One barrier closes the trajectory: it publishes the new unvisited counts for the next seed draw AND orders the
     // centre update below after every CTA's read of `centres` above.
     publish_unvisited(st, lo, hi, b, s_int);
-    grid.sync();
+    grid_sync();
     if (b == 0 && tid < D && room) {
       double* c = st.centres + (size_t)cid * D;
       c[tid] = merged ? 0.5 * (c[tid] + s_mean[tid]) : s_mean[tid];  // MS.h:113 / :118
@@ -296,9 +304,10 @@ mh_status launch_meanshift(mh_ctx* ctx, const double* d_feat, int N, int D, doub
   MH_CUDA(ctx, cudaDeviceGetAttribute(&dev_coop, cudaDevAttrCooperativeLaunch, ctx->device));
   if (!dev_coop) return fail(ctx, MH_ECUDA, "device lacks cooperative launch");
   int per_sm = 0;
-  MH_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, meanshift_kernel, MS_THREADS, 0));
+  MH_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, meanshift_kernel<false>, MS_THREADS, 0));
   if (per_sm < 1) return fail(ctx, MH_ECUDA, "meanshift kernel does not fit an SM");
-  int blocks = std::min(ctx->sm_count, (N + MS_THREADS - 1) / MS_THREADS);
+  const bool single = N <= MS_SINGLE_MAX;
+  int blocks = single ? 1 : std::min(ctx->sm_count, (N + MS_THREADS - 1) / MS_THREADS);
   blocks = std::max(1, blocks);
 
   const int Npad = (N + 31) & ~31;
@@ -345,9 +354,14 @@ mh_status launch_meanshift(mh_ctx* ctx, const double* d_feat, int N, int D, doub
   ms_transpose_kernel<<<(N + 255) / 256, 256, 0, ctx->stream>>>(d_feat, N, Npad, D, (double*)(base + o_dataT), st.visited,
                                                                 st.vl_n);
   MH_LAUNCHED(ctx, "ms_transpose_kernel");
-  void* args[] = {&st};
-  MH_CUDA(ctx, cudaLaunchCooperativeKernel((void*)meanshift_kernel, dim3(blocks), dim3(MS_THREADS), args, 0, ctx->stream));
-  ++ctx->launches;
+  if (single) {
+    meanshift_kernel<true><<<1, MS_THREADS, 0, ctx->stream>>>(st);
+    MH_LAUNCHED(ctx, "meanshift_kernel<single>");
+  } else {
+    void* args[] = {&st};
+    MH_CUDA(ctx, cudaLaunchCooperativeKernel((void*)meanshift_kernel<false>, dim3(blocks), dim3(MS_THREADS), args, 0, ctx->stream));
+    ++ctx->launches;
+  }
   struct { int32_t C, overflow, pad0, pad1; unsigned long long traj, iters; uint32_t rng; } out;
   MH_CUDA(ctx, cudaMemcpyAsync(&out, base + o_out, 36, cudaMemcpyDeviceToHost, ctx->stream));
   MH_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

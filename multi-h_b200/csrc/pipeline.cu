@@ -30,10 +30,11 @@ using namespace mh;
 
 namespace {
 
-struct DevBuf {  // grow-only device buffer: the alternating loop re-uses its buffers instead of cudaMalloc/cudaFree per step
-  void* p = nullptr;
-  uint64_t cap = 0;
-  ~DevBuf() { if (p) cudaFree(p); }
+struct DevBuf {  // grow-only device buffer owned by the context (slot of mh_ctx::pbuf): mh_process allocates on the first pair
+                 // of a size class and re-uses the buffers afterwards — no cudaMalloc/cudaFree in steady state
+  void*& p;
+  uint64_t& cap;
+  DevBuf(mh_ctx* ctx, int slot) : p(ctx->pbuf[slot]), cap(ctx->pcap[slot]) {}
   mh_status alloc(mh_ctx* ctx, uint64_t bytes) {
     bytes = std::max<uint64_t>(bytes, 256);
     if (p && cap >= bytes) return MH_OK;
@@ -87,8 +88,13 @@ mh_status mh_process(mh_ctx* ctx, const double* pts, const double* aff, const do
   ctx->rng_state = P.rng_seed;  // every Process() call starts from the same generator state, like a fresh run of the reference
   MH_TRY(mh_set_geometry(ctx, F, nullptr, nullptr, pts, N));
 
-  DevBuf b_pts, b_aff, b_pts64, b_aff64, b_raw_p, b_raw_a, b_keepmask, b_hyp_pt, b_hyp_pt64, b_feat, b_centres, b_assign, b_hyp,
-      b_hyp64, b_keep, b_cost, b_labels, b_modes_hyp, b_modes_hyp64, b_feat6, b_scatter;
+  int slot = 0;
+  DevBuf b_pts(ctx, slot++), b_aff(ctx, slot++), b_pts64(ctx, slot++), b_aff64(ctx, slot++), b_raw_p(ctx, slot++),
+      b_raw_a(ctx, slot++), b_keepmask(ctx, slot++), b_hyp_pt(ctx, slot++), b_hyp_pt64(ctx, slot++), b_feat(ctx, slot++),
+      b_centres(ctx, slot++), b_assign(ctx, slot++), b_hyp(ctx, slot++), b_hyp64(ctx, slot++), b_keep(ctx, slot++),
+      b_cost(ctx, slot++), b_labels(ctx, slot++), b_modes_hyp(ctx, slot++), b_modes_hyp64(ctx, slot++), b_feat6(ctx, slot++),
+      b_scatter(ctx, slot++);
+  static_assert(sizeof(((mh_ctx*)nullptr)->pbuf) / sizeof(void*) >= 21, "mh_ctx::pbuf has a slot per mh_process buffer");
   const int32_t N_in = N;
   std::vector<int32_t> keepmask;      // prefilter survivors (only with params.prefilter)
   std::vector<double> kept_pts_host;  // their refined coordinates, for the host neighbourhood search
@@ -176,9 +182,15 @@ mh_status mh_process(mh_ctx* ctx, const double* pts, const double* aff, const do
   t0 = now_ms();
   std::vector<int64_t> offsets((size_t)N + 1);
   int64_t total = 0;
-  MH_TRY(mh_neighbourhood(ctx, pts, N, 1.0 / P.locality, P.max_neighbours, offsets.data(), nullptr, &total));
-  std::vector<int32_t> adj((size_t)std::max<int64_t>(total, 1));
-  MH_TRY(mh_neighbourhood(ctx, pts, N, 1.0 / P.locality, P.max_neighbours, offsets.data(), adj.data(), &total));
+  std::vector<int32_t> adj;
+  if (P.max_neighbours > 0) {   // list lengths are bounded: one pass into a buffer of the bound
+    adj.resize((size_t)N * (size_t)P.max_neighbours + 1);
+    MH_TRY(mh_neighbourhood(ctx, pts, N, 1.0 / P.locality, P.max_neighbours, offsets.data(), adj.data(), &total));
+  } else {                      // full ball: count, then fill
+    MH_TRY(mh_neighbourhood(ctx, pts, N, 1.0 / P.locality, P.max_neighbours, offsets.data(), nullptr, &total));
+    adj.resize((size_t)std::max<int64_t>(total, 1));
+    MH_TRY(mh_neighbourhood(ctx, pts, N, 1.0 / P.locality, P.max_neighbours, offsets.data(), adj.data(), &total));
+  }
   ctx->stage_ms[2] = now_ms() - t0;
 
   // uploads the current hypothesis set (both representations)

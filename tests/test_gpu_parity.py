@@ -305,6 +305,21 @@ def test_k3_meanshift_and_k4_3pt_vs_oracle(mh, orc):
     assert cen6.shape[1] == 6 and cen6.shape[0] >= 1
 
 
+def test_k3_meanshift_cooperative_path_vs_oracle(mh, orc):
+    """N > 4096 takes the persistent cooperative kernel (chip-wide passes, grid barriers); N <= 4096 above takes the one-CTA
+    variant.  Same statement for both: the oracle's trajectories, window iterations and centres."""
+    import torch
+
+    sc = mh.scenes.make_scene(5000, 6, seed=11)
+    ctx = mh.Context()
+    fo = orc.features10(orc.haf_hypotheses(sc.pts, sc.aff, sc.F), sc.pts, 0.005)
+    cen, asg, st = ctx.meanshift(torch.from_numpy(fo).cuda(), 2.2)
+    co, ao, _, sto = orc.meanshift(fo, 2.2)
+    assert st == sto and cen.shape[0] == co.shape[0]
+    assert np.abs(cen.cpu().numpy() - co).max() <= 1e-6
+    assert (asg.cpu().numpy() == ao).mean() >= 0.999
+
+
 def _ari(a, b):
     """adjusted Rand index of two labelings (label ids may be permuted between runs)"""
     a = np.unique(a, return_inverse=True)[1]; b = np.unique(b, return_inverse=True)[1]
