@@ -157,6 +157,11 @@ mh_status mh_features6(mh_ctx* ctx, const void* d_hyp, int32_t K, void* d_feat /
 /* MeanShiftClustering<double>::Cluster (MeanShiftClustering.h:22-157): sequential-seed flat-kernel mean-shift, run as ONE
  * persistent cooperative kernel in FP64 (seeds drawn by the restated MSVC rand()).  d_centres f64 [max_c][D],
  * d_assign i32 [N] (cluster with most votes, first wins ties).  *C_out = number of centres. */
+/* A mean-shift trajectory ends after this many window iterations at the latest (the reference's `while (1)`,
+ * MeanShiftClustering.h:62-124, never returns when the mean cycles — possible with its L1 window; observed on synthetic
+ * 5000-correspondence scenes). */
+#define MH_MS_MAX_WINDOW_ITERS 200
+
 /* The seed generator's state persists across mh_meanshift calls of a context (as rand() does in the reference process);
  * mh_process re-seeds it from params.rng_seed on entry. */
 mh_status mh_set_rng_state(mh_ctx* ctx, uint32_t state);

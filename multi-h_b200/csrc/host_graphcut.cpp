@@ -358,15 +358,19 @@ class MovePool {
     busy_ = false;   // only the owner of busy_ writes it back; acquire() reads it under the global mutex
   }
   int threads() const { return (int)th_.size() + 1; }
-  // fn(job, thread) for job in [0, n): the caller takes part as thread 0
+  // fn(job, thread) for job in [0, n): the caller takes part as thread 0.  The epoch is a sequence lock: odd while the
+  // caller rewrites the job state, which it does only after every worker has left work() (active_ == 0); a worker registers
+  // in active_ first and re-checks the epoch, so it can never run on half-written state or on a finished run's counters.
   template <typename F> void run(int n, F&& fn) {
+    epoch_.fetch_add(1);                        // odd: no new worker may enter
+    while (active_.load() != 0) cpu_relax();    // stragglers of the previous run leave
     fn_ = [&](int j, int t) { fn(j, t); };
     njobs_ = n;
-    done_.store(0, std::memory_order_relaxed);
-    next_.store(0, std::memory_order_relaxed);
-    epoch_.fetch_add(1, std::memory_order_release);
+    done_.store(0);
+    next_.store(0);
+    epoch_.fetch_add(1);                        // even: go
     work(0);
-    while (done_.load(std::memory_order_acquire) < n) cpu_relax();
+    while (done_.load() < n) cpu_relax();
   }
 
  private:
@@ -394,23 +398,26 @@ class MovePool {
   }
   void end_session() {
     { std::lock_guard<std::mutex> lk(m_); session_ = false; }
-    epoch_.fetch_add(1, std::memory_order_release);   // spinners re-check the session flag
+    epoch_.fetch_add(2);   // (stays even) spinners re-check the session flag
   }
   void loop(int t) {
-    uint64_t seen = epoch_.load(std::memory_order_acquire);
+    uint64_t seen = epoch_.load();
     for (;;) {
       {
         std::unique_lock<std::mutex> lk(m_);
         cv_.wait(lk, [this] { return session_; });
       }
       for (;;) {   // inside a session: spin on the epoch
-        const uint64_t e = epoch_.load(std::memory_order_acquire);
-        if (e != seen) {
+        const uint64_t e = epoch_.load();
+        if (e != seen && (e & 1) == 0) {
+          active_.fetch_add(1);
+          if (epoch_.load() != e) { active_.fetch_sub(1); continue; }   // the caller moved on: look again
           seen = e;
           bool in_session;
           { std::lock_guard<std::mutex> lk(m_); in_session = session_; }
+          if (in_session) work(t);
+          active_.fetch_sub(1);
           if (!in_session) break;
-          work(t);
         } else {
           cpu_relax();
         }
@@ -421,10 +428,10 @@ class MovePool {
   std::mutex m_;
   std::condition_variable cv_;
   bool session_ = false;
-  bool busy_ = false;
+  std::atomic<bool> busy_{false};
   std::function<void(int, int)> fn_;
   int njobs_ = 0;
-  std::atomic<int> next_{0}, done_{0};
+  std::atomic<int> next_{0}, done_{0}, active_{0};
   std::atomic<uint64_t> epoch_{0};
 };
 

@@ -76,6 +76,7 @@ __global__ void ms_transpose_kernel(const double* __restrict__ data, int N, int 
 }
 
 // number of not-yet-visited points of [lo, hi) -> block_unvisited[b]
+template <int MS_THREADS>
 __device__ __forceinline__ void publish_unvisited(const MsState& st, int lo, int hi, int b, int* s_int) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   int c = 0;
@@ -92,10 +93,11 @@ __device__ __forceinline__ void publish_unvisited(const MsState& st, int lo, int
 }
 
 // SINGLE: the whole problem fits one CTA's stride loop (N <= MS_SINGLE_MAX: the bundled pairs' 1-2k correspondences, and
-// every merging step's K hypotheses) — a plain launch whose "grid barrier" is __syncthreads(): ~1 us per window iteration
+// every merging step's K hypotheses, cfg5's 5k-correspondence pairs) — a plain launch whose "grid barrier" is __syncthreads(): ~1 us per window iteration
 // instead of ~5 us, which is what the latency-bound small cases pay for.
-constexpr int MS_SINGLE_MAX = 4096;
-template <bool SINGLE>
+constexpr int MS_SINGLE_MAX = 8192;
+constexpr int MS_SINGLE_THREADS = 512;
+template <bool SINGLE, int MS_THREADS>
 __global__ void __launch_bounds__(MS_THREADS) meanshift_kernel(MsState st) {
   auto grid_sync = [] {
     if constexpr (SINGLE) __syncthreads();
@@ -117,7 +119,7 @@ __global__ void __launch_bounds__(MS_THREADS) meanshift_kernel(MsState st) {
   unsigned long long traj = 0, iters = 0;
   int overflow = 0;
 
-  publish_unvisited(st, lo, hi, b, s_int);
+  publish_unvisited<MS_THREADS>(st, lo, hi, b, s_int);
   grid_sync();
   for (;;) {
     // ---- every CTA derives the same seed rank (MS.h:54-56) -------------------------
@@ -165,7 +167,10 @@ __global__ void __launch_bounds__(MS_THREADS) meanshift_kernel(MsState st) {
     ++traj;
 
     // ---- window iterations (MS.h:62-98) -------------------------------------------
-    for (;;) {
+    // The reference loops until the mean stops moving; with its L1 window the mean can cycle and the reference never
+    // returns (oracle/multih_oracle.cpp orc_meanshift).  A trajectory ends after MH_MS_MAX_WINDOW_ITERS iterations at the
+    // latest, keeping its current mean — identical in oracle and product.
+    for (int window_iters = 1;; ++window_iters) {
       const int par = (int)(iters & 1ull);
       ++iters;
       double acc[MS_MAXD + 1];
@@ -228,7 +233,7 @@ __global__ void __launch_bounds__(MS_THREADS) meanshift_kernel(MsState st) {
       __syncthreads();
       if (tid < D) s_mean[tid] = nm[tid];
       __syncthreads();
-      if (sqrt(n2) < st.stopThresh || !(cnt > 0.0)) break;  // MS.h:98 (cnt == 0 cannot happen for finite seeds)
+      if (sqrt(n2) < st.stopThresh || !(cnt > 0.0) || window_iters >= MH_MS_MAX_WINDOW_ITERS) break;  // MS.h:98 (cnt == 0 cannot happen for finite seeds)
     }
 
     // ---- merge into the first centre closer than bw/2, else append (MS.h:100-120) ---
@@ -268,7 +273,7 @@ __global__ void __launch_bounds__(MS_THREADS) meanshift_kernel(MsState st) {
     else overflow = 1;
     // One barrier closes the trajectory: it publishes the new unvisited counts for the next seed draw AND orders the
     // centre update below after every CTA's read of `centres` above.
-    publish_unvisited(st, lo, hi, b, s_int);
+    publish_unvisited<MS_THREADS>(st, lo, hi, b, s_int);
     grid_sync();
     if (b == 0 && tid < D && room) {
       double* c = st.centres + (size_t)cid * D;
@@ -304,7 +309,7 @@ mh_status launch_meanshift(mh_ctx* ctx, const double* d_feat, int N, int D, doub
   MH_CUDA(ctx, cudaDeviceGetAttribute(&dev_coop, cudaDevAttrCooperativeLaunch, ctx->device));
   if (!dev_coop) return fail(ctx, MH_ECUDA, "device lacks cooperative launch");
   int per_sm = 0;
-  MH_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, meanshift_kernel<false>, MS_THREADS, 0));
+  MH_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, meanshift_kernel<false, MS_THREADS>, MS_THREADS, 0));
   if (per_sm < 1) return fail(ctx, MH_ECUDA, "meanshift kernel does not fit an SM");
   const bool single = N <= MS_SINGLE_MAX;
   int blocks = single ? 1 : std::min(ctx->sm_count, (N + MS_THREADS - 1) / MS_THREADS);
@@ -355,11 +360,12 @@ mh_status launch_meanshift(mh_ctx* ctx, const double* d_feat, int N, int D, doub
                                                                 st.vl_n);
   MH_LAUNCHED(ctx, "ms_transpose_kernel");
   if (single) {
-    meanshift_kernel<true><<<1, MS_THREADS, 0, ctx->stream>>>(st);
+    if (N <= 1024) meanshift_kernel<true, MS_THREADS><<<1, MS_THREADS, 0, ctx->stream>>>(st);
+    else meanshift_kernel<true, MS_SINGLE_THREADS><<<1, MS_SINGLE_THREADS, 0, ctx->stream>>>(st);
     MH_LAUNCHED(ctx, "meanshift_kernel<single>");
   } else {
     void* args[] = {&st};
-    MH_CUDA(ctx, cudaLaunchCooperativeKernel((void*)meanshift_kernel<false>, dim3(blocks), dim3(MS_THREADS), args, 0, ctx->stream));
+    MH_CUDA(ctx, cudaLaunchCooperativeKernel((void*)meanshift_kernel<false, MS_THREADS>, dim3(blocks), dim3(MS_THREADS), args, 0, ctx->stream));
     ++ctx->launches;
   }
   struct { int32_t C, overflow, pad0, pad1; unsigned long long traj, iters; uint32_t rng; } out;

@@ -319,6 +319,7 @@ void orc_features6(const double* H, int64_t K, double* out) {
 // occurs unless no votes); votes_out optional.  Also reports trajectory and
 // window-iteration counts.
 // ---------------------------------------------------------------------------
+constexpr int MS_MAX_WINDOW_ITERS = 200;   // = MH_MS_MAX_WINDOW_ITERS of include/multih_b200.h
 int orc_meanshift(const double* data, int N, int D, double bw, int metric, uint32_t* rng_state, double* centres,
                   int max_c, int* assign, int64_t* stats /*[2]: trajectories, iterations*/) {
   const double bandSq = bw * bw, stopThresh = 1e-3 * bw;
@@ -339,8 +340,10 @@ int orc_meanshift(const double* data, int N, int D, double bw, int metric, uint3
     for (int j = 0; j < D; ++j) myMean[j] = data[(size_t)stInd * D + j];
     std::vector<int> votes(N, 0);
     ++traj;
+    int window_iters = 0;
     while (true) {
       ++iters;
+      ++window_iters;
       oldMean = myMean;
       std::fill(acc.begin(), acc.end(), 0.0);
       int cnt = 0;
@@ -359,7 +362,11 @@ int orc_meanshift(const double* data, int N, int D, double bw, int metric, uint3
       for (int j = 0; j < D; ++j) myMean[j] = acc[j] / cnt;  // cnt==0 -> NaN as in the reference (cannot occur: seed is a member)
       double n2 = 0;
       for (int j = 0; j < D; ++j) n2 += (myMean[j] - oldMean[j]) * (myMean[j] - oldMean[j]);
-      if (std::sqrt(n2) < stopThresh) {
+      // MS.h:98 loops `while (1)` until the mean stops moving.  With an L1 window and a flat kernel the mean can enter a
+      // cycle (e.g. synthetic scene seed 0xB200 + 33, 5000 correspondences) and the reference never returns; oracle and
+      // product stop a trajectory after MS_MAX_WINDOW_ITERS window iterations and keep its current mean — a deviation
+      // only on inputs on which the reference hangs.
+      if (std::sqrt(n2) < stopThresh || window_iters >= MS_MAX_WINDOW_ITERS) {
         int mergeWith = -1;
         for (size_t cn = 0; cn < clustCent.size(); ++cn) {
           double d2 = 0;
@@ -375,7 +382,6 @@ int orc_meanshift(const double* data, int N, int D, double bw, int metric, uint3
         }
         break;
       }
-      if (iters > 100000000) break;  // guard only
     }
     initPtInds.clear();
     for (int i = 0; i < N; ++i)

@@ -306,16 +306,30 @@ def test_k3_meanshift_and_k4_3pt_vs_oracle(mh, orc):
 
 
 def test_k3_meanshift_cooperative_path_vs_oracle(mh, orc):
-    """N > 4096 takes the persistent cooperative kernel (chip-wide passes, grid barriers); N <= 4096 above takes the one-CTA
+    """N > 8192 takes the persistent cooperative kernel (chip-wide passes, grid barriers); N <= 8192 above takes the one-CTA
     variant.  Same statement for both: the oracle's trajectories, window iterations and centres."""
     import torch
 
-    sc = mh.scenes.make_scene(5000, 6, seed=11)
+    sc = mh.scenes.make_scene(9000, 6, seed=11)
     ctx = mh.Context()
     fo = orc.features10(orc.haf_hypotheses(sc.pts, sc.aff, sc.F), sc.pts, 0.005)
     cen, asg, st = ctx.meanshift(torch.from_numpy(fo).cuda(), 2.2)
     co, ao, _, sto = orc.meanshift(fo, 2.2)
     assert st == sto and cen.shape[0] == co.shape[0]
+    assert np.abs(cen.cpu().numpy() - co).max() <= 1e-6
+    assert (asg.cpu().numpy() == ao).mean() >= 0.999
+
+
+def test_k3_meanshift_cycling_trajectory_is_capped_like_the_oracle(mh, orc):
+    """On this scene a trajectory of the reference algorithm cycles (the reference's `while (1)` never returns): oracle and
+    kernel end it after MH_MS_MAX_WINDOW_ITERS window iterations, in lockstep — same trajectories, iterations, centres."""
+    import torch
+
+    sc = mh.scenes.make_scene(5000, 3 + (29 % 6), seed=0xB200 + 4 + 29)
+    fo = orc.features10(orc.haf_hypotheses(sc.pts, sc.aff, sc.F), sc.pts, 0.005)
+    co, ao, _, sto = orc.meanshift(fo, 2.2)
+    cen, asg, st = mh.Context().meanshift(torch.from_numpy(fo).cuda(), 2.2)
+    assert st == sto and cen.shape[0] == co.shape[0], (st, sto)
     assert np.abs(cen.cpu().numpy() - co).max() <= 1e-6
     assert (asg.cpu().numpy() == ao).mean() >= 0.999
 

@@ -152,3 +152,14 @@ def test_prefilter_golden(orc):
         assert np.abs(ao - g[f"{name}_out_aff"]).max() < 1e-8
     # the hot-path input fixture is exactly the survivors of the F-RANSAC inliers
     assert g["barr_keep"].sum() >= 1197
+
+
+def test_meanshift_terminates_on_a_cycling_trajectory(orc):
+    """The reference's mean-shift loops `while (1)` (MeanShiftClustering.h:62) and never returns when the mean cycles; the
+    oracle (and the kernel) cap a trajectory at MH_MS_MAX_WINDOW_ITERS window iterations.  This scene cycles."""
+    import multih_b200 as m
+
+    sc = m.scenes.make_scene(5000, 3 + (29 % 6), seed=0xB200 + 4 + 29)
+    fo = orc.features10(orc.haf_hypotheses(sc.pts, sc.aff, sc.F), sc.pts, 0.005)
+    cen, asg, _, st = orc.meanshift(fo, 2.2)
+    assert st[0] > 0 and st[1] >= 200 and len(cen) > 10 and (asg >= 0).all()
