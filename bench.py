@@ -267,6 +267,15 @@ def main():
     sampler.start()
     launches0 = ctx.launches
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    align = torch.zeros(1, device=dev)
+
+    def align_ranks():
+        # the host barrier releases the ranks up to a millisecond apart; a one-element all-reduce on the compute stream makes
+        # the ranks' STREAMS start the timed region together (outside the timed region: it precedes the opening event)
+        if world > 1:
+            dist.all_reduce(align)
+
+    align_ranks()
     t0.record()
     for i in range(args.steps):
         hot_pass(k2_ev[args.warmup + i])
@@ -292,6 +301,7 @@ def main():
         e2e_pass()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    align_ranks()
     e0.record()
     for _ in range(args.steps):
         e2e_pass()
