@@ -511,36 +511,65 @@ mh_status alpha_expansion(const int32_t* cost, int N, int L, int potts, const in
   MoveWS* const wsp = ws.data();          // (thread_local objects: workers must go through the caller's pointers)
   MoveResult* const resp = res.data();
 
-  std::vector<int> changed;   // sites committed since the window's snapshot
+  // Move memo.  Right after move alpha has been processed the labelling admits no improving alpha-expansion, and what a
+  // re-evaluation would read lies inside the `touched` set of that evaluation (the candidates only shrink by the sites that
+  // switched).  So when alpha comes round again and none of the sites that changed in between is in that set or newly
+  // qualifies as a candidate, the move is known to change nothing and is not evaluated at all — most moves of the later
+  // cycles.  `log` lists the changed sites in commit order; memo[alpha].pos = its length when alpha was last processed.
+  struct Memo { bool valid = false, any_c0 = false; size_t pos = 0; std::vector<uint64_t> touched; };
+  std::vector<Memo> memo(L);
+  std::vector<int> log;
+  auto clean_since = [&](int alpha, const std::vector<uint64_t>& touched, bool any_c0, size_t from) {
+    for (size_t k = from; k < log.size(); ++k) {
+      const int d = log[k];
+      if (any_c0 && ((touched[(size_t)d >> 6] >> (d & 63)) & 1ull)) return false;
+      if (lab[d] != alpha && (int64_t)cost[(size_t)d * L + alpha] - cost[(size_t)d * L + lab[d]] <= Wall[d]) return false;
+    }
+    return true;
+  };
+  auto known_idle = [&](int alpha) {
+    Memo& m = memo[alpha];
+    if (!m.valid || log.size() - m.pos > (size_t)N) return false;   // (a long log: evaluating is cheaper than checking)
+    if (!clean_since(alpha, m.touched, m.any_c0, m.pos)) return false;
+    m.pos = log.size();
+    return true;
+  };
+
   if (max_cycles < 0) max_cycles = 1 << 30;
   const int64_t max_moves = (int64_t)std::min<int64_t>(max_cycles, (1LL << 40) / L) * L;
   int idle_moves = 0;   // consecutive moves that changed nothing: L of them = a full sweep over an unchanged labelling
-  int64_t E_cycle = 0, E_delta = 0;   // energy change within the current cycle (GCO stops after a cycle without change)
-  (void)E_cycle;
+  int64_t E_delta = 0;  // energy change within the current cycle (GCO stops after a cycle without change)
   int64_t move = 0;
   bool stop = false;
+  std::vector<char> speculated(window);
   while (!stop && move < max_moves && idle_moves < L) {
     const int nw = (int)std::min<int64_t>(window, max_moves - move);
     const int a0 = (int)(move % L);
-    if (pool && nw > 1)
-      pool->run(nw, [&, wsp, resp](int j, int t) { eval_move(P, lab, (a0 + j) % L, wsp[t], resp[j], true); });
-    changed.clear();
+    const size_t snapshot = log.size();   // speculative results below are evaluated on the labelling at this point
+    if (pool && nw > 1) {
+      int todo = 0;
+      for (int j = 0; j < nw; ++j) todo += (speculated[j] = !known_idle((a0 + j) % L));
+      if (todo > 1)
+        pool->run(nw, [&, wsp, resp](int j, int t) {
+          if (speculated[j]) eval_move(P, lab, (a0 + j) % L, wsp[t], resp[j], true);
+        });
+      else
+        std::fill(speculated.begin(), speculated.end(), 0);
+    }
     for (int j = 0; j < nw && !stop; ++j, ++move) {
       const int alpha = (a0 + j) % L;
-      bool valid = pool && nw > 1;
-      if (valid && !changed.empty()) {
-        const MoveResult& r = res[j];
-        for (int d : changed) {
-          if (r.any_c0 && ((r.touched[(size_t)d >> 6] >> (d & 63)) & 1ull)) { valid = false; break; }
-          if (lab[d] != alpha && (int64_t)cost[(size_t)d * L + alpha] - cost[(size_t)d * L + lab[d]] <= Wall[d]) { valid = false; break; }
-        }
-      }
-      if (!valid) eval_move(P, lab, alpha, ws[0], res[j], false);
       ++idle_moves;
-      if (!res[j].sw.empty()) {
-        for (int i : res[j].sw) { lab[i] = alpha; changed.push_back(i); }
-        E_delta += res[j].delta;
-        idle_moves = 0;
+      if (!known_idle(alpha)) {
+        const bool usable = pool && nw > 1 && speculated[j] && clean_since(alpha, res[j].touched, res[j].any_c0, snapshot);
+        if (!usable) eval_move(P, lab, alpha, ws[0], res[j], true);
+        if (!res[j].sw.empty()) {
+          for (int i : res[j].sw) { lab[i] = alpha; log.push_back(i); }
+          E_delta += res[j].delta;
+          idle_moves = 0;
+        }
+        Memo& m = memo[alpha];
+        m.valid = true; m.any_c0 = res[j].any_c0; m.pos = log.size();
+        m.touched.swap(res[j].touched);
       }
       if (alpha == L - 1) {   // end of a cycle: GCO stops when the cycle left the energy unchanged
         if (E_delta == 0) stop = true;

@@ -64,6 +64,37 @@ def test_alpha_expansion_equals_reference_gco(mh, orc, radius):
     assert e2 == e_ref2 and np.array_equal(l2, l_ref2)
 
 
+@pytest.mark.parametrize("threads", ["1", "8"])
+def test_alpha_expansion_random_problems_equal_reference_gco(mh, orc, threads, monkeypatch):
+    """Randomised check of everything the host expansion does beyond a plain max-flow per move — exact candidate reduction,
+    move memo, speculative parallel evaluation (MH_GC_THREADS) — against the reference GCO: random graphs (multi-edges,
+    isolated sites), coarse costs with many ties, zero / huge Potts weights, cold and warm starts, capped cycles."""
+    if orc.ref_lib() is None:
+        pytest.skip("oracle/_ref not built")
+    monkeypatch.setenv("MH_GC_THREADS", threads)
+    rng = np.random.default_rng(1234)
+    for trial in range(60):
+        N = int(rng.integers(2, 400))
+        L = int(rng.integers(2, 24))
+        levels = int(rng.choice([2, 5, 200, 9802]))
+        cost = rng.integers(0, levels + 1, size=(N, L)).astype(np.int32)
+        if trial % 3 == 0:   # planted structure: blocks of sites prefer one label
+            pref = rng.integers(0, L, size=N // 8 + 1).repeat(8)[:N]
+            cost[np.arange(N), pref] = 0
+        deg = rng.integers(0, 7, size=N)
+        off = np.concatenate([[0], np.cumsum(deg)]).astype(np.int64)
+        adj = rng.integers(0, N, size=int(off[-1])).astype(np.int32)    # may repeat, may hit the site itself
+        near = rng.random(len(adj)) < 0.7                               # mostly local edges
+        src = np.repeat(np.arange(N), deg)
+        adj[near] = np.clip(src[near] + rng.integers(-3, 4, size=int(near.sum())), 0, N - 1)
+        potts = int(rng.choice([0, 1, 50, 137, 5000]))
+        init = None if trial % 2 == 0 else rng.integers(0, L, size=N).astype(np.int32)
+        cycles = 1000 if trial % 5 else 2
+        e_ref, l_ref = orc.gco_ref_expansion(cost, potts, off, adj, init_labels=init, max_iter=cycles)
+        l, e = mh.capi.alpha_expansion(cost, potts, off, adj, init=init, max_cycles=cycles)
+        assert e == e_ref and np.array_equal(l, l_ref), (trial, N, L, levels, potts, cycles)
+
+
 def test_alpha_expansion_edge_cases(mh):
     cost = np.array([[5, 1, 9], [2, 2, 2], [9, 8, 7]], dtype=np.int32)
     l, e = mh.capi.alpha_expansion(cost, 50, np.zeros(4, dtype=np.int64), np.zeros(0, dtype=np.int32))
