@@ -114,3 +114,38 @@ def test_text_format_roundtrip(mh, tmp_path):
     pts, aff, lab = mh.scenes.load_points(str(p))
     assert np.allclose(pts, sc.pts, rtol=1e-5) and np.allclose(aff, sc.aff, rtol=1e-5, atol=1e-6)
     assert np.array_equal(lab, sc.gt)
+
+
+def test_cpp_shim_compiles_links_and_fails_loudly_without_a_gpu(mh, tmp_path):
+    """include/multih_b200.hpp (the reference's class surface over the C ABI) builds against the library with plain g++, and a
+    C99 translation unit can include the C header.  Run here (no GPU) the shim's constructor must throw: no CPU fallback."""
+    import shutil
+    import subprocess
+
+    if shutil.which("g++") is None:
+        pytest.skip("no g++")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    inc, libdir = os.path.join(root, "include"), os.path.dirname(mh.library_path())
+    src = tmp_path / "shim.cpp"
+    src.write_text(
+        '#include "multih_b200.hpp"\n'
+        "int main() {\n"
+        "  try { multih_b200::MultiH m(2.6, 2.2, 0.005, 0.5, 20); std::vector<int> l; m.GetLabels(l);\n"
+        "        std::printf(\"ctx %d %d\\n\", m.GetPointNumber(), m.GetClusterNumber()); return 0; }\n"
+        "  catch (const std::exception& e) { std::printf(\"threw: %s\\n\", e.what()); return 3; }\n"
+        "}\n")
+    exe = tmp_path / "shim"
+    subprocess.run(["g++", "-std=c++17", "-I", inc, str(src), "-L", libdir, "-lmultih_b200", f"-Wl,-rpath,{libdir}", "-o", str(exe)],
+                   check=True)
+    csrc = tmp_path / "abi.c"
+    csrc.write_text('#include "multih_b200.h"\nint main(void) { mh_params p; mh_default_params(&p); return p.lambda == 0.5 ? 0 : 1; }\n')
+    subprocess.run(["gcc", "-std=c99", "-I", inc, str(csrc), "-L", libdir, "-lmultih_b200", f"-Wl,-rpath,{libdir}", "-o", str(tmp_path / "abi")],
+                   check=True)
+    assert subprocess.run([str(tmp_path / "abi")]).returncode == 0
+    import torch
+
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    if torch.cuda.is_available():
+        assert r.returncode == 0 and "ctx 0 0" in r.stdout
+    else:
+        assert r.returncode == 3 and "no CPU fallback" in r.stdout
