@@ -123,6 +123,21 @@ def run_reference(args):
                                    f"inlier count, FP64 oracle port, {cores} threads)"},
         "e2e": {"value": value, "unit": "residuals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
+    # second half of the metric on the CPU arm: the bundled pair through the oracle's restatement of MultiH::Process with the
+    # reference's own alpha-expansion (oracle/_ref, GCO compiled in place), one run
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        from ref_pipeline import oracle_process
+
+        g = np.load(os.path.join(ROOT, "tests", "golden", "barrsmith_hotpath_input.npz"))
+        tr = time.perf_counter()
+        rlab, rH, rinfo = oracle_process(g["pts"], g["aff"], g["F"])
+        line["pair_e2e"] = {"workload": "bundled barrsmith pair, hot-path input fixture (1197 correspondences)",
+                            "ms_per_pair": (time.perf_counter() - tr) * 1e3, "planes": int(len(rH)),
+                            "iterations": int(rinfo["iterations"]),
+                            "kind": "oracle pipeline (FP64 port) + reference GCO alpha-expansion"}
+    except Exception as e:
+        line["pair_e2e"] = {"unavailable": repr(e)}
     print(json.dumps(line), flush=True)
 
 
