@@ -196,7 +196,9 @@ mh_status mh_modes_to_hypotheses(mh_ctx* ctx, const void* d_modes /*f64 [C][6]*/
 /* ---- host combinatorial steps (consume GPU-built costs) ------------------- */
 /* 4-D neighbourhood replacing FlannBasedMatcher::radiusMatch (MultiH.cpp:231-253): per site the `max_neighbours`
  * nearest other sites (ties by index) with d^2 <= radius^2 on float (x1,y1,x2,y2); <= 0 = full ball.  Directed CSR out,
- * ascending neighbour index; call with adj_host == NULL to size.  Host-only: ctx may be NULL. */
+ * ascending neighbour index; call with adj_host == NULL to size (or pass N * max_neighbours entries).  ctx may be NULL: host
+ * grid search.  With a context and 1 <= max_neighbours <= 64 the search runs on the GPU for N >= 256 (K5):
+ * the same set, bit for bit (mh_diag_set_neighbourhood_backend forces either). */
 mh_status mh_neighbourhood(mh_ctx* ctx, const double* pts_host, int32_t N, double radius, int32_t max_neighbours,
                            int64_t* offsets_host, int32_t* adj_host, int64_t* total_out);
 /* Alpha-expansion (the role of GCoptimizationGeneralGraph in MultiH.cpp:520-543; own implementation, int64 totals):
@@ -233,6 +235,8 @@ int32_t mh_diag_get_fast_config(mh_ctx* ctx);
 /* 1 = tiled dense-cost kernel with TMA row stores (default; float->int through a denormal product), 2 / 3 = same kernel with
  * the 2^23-magic / F2I conversion, 0 = first-generation scalar-store kernel (A/B evidence) */
 mh_status mh_diag_set_dense_variant(mh_ctx* ctx, int32_t variant);
+/* mh_neighbourhood backend: 0 = auto, 1 = host, 2 = device */
+mh_status mh_diag_set_neighbourhood_backend(mh_ctx* ctx, int32_t backend);
 /* where the alternating optimisation of the last mh_process spent its time, ms: [0] mean-shift of the hypotheses
  * [1] mode fit + inlier scan + straightness [2] data-cost matrix (+ D2H) [3] host alpha-expansion [4] refit */
 mh_status mh_diag_get_alternating_ms(const mh_ctx* ctx, double ms[5]);

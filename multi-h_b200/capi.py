@@ -27,7 +27,7 @@ SYMBOLS = [
     "mh_hypotheses_to_host", "mh_prefilter", "mh_prefilter_device", "mh_haf_hypotheses", "mh_data_cost_dense", "mh_residuals", "mh_data_cost_fused",
     "mh_inlier_stats", "mh_inliers_of_homography", "mh_features10", "mh_features6", "mh_set_rng_state", "mh_get_rng_state", "mh_meanshift", "mh_refit_haf",
     "mh_refit_haf_accumulate", "mh_refit_haf_solve", "mh_labels_from_best", "mh_pack_inlier_counts", "mh_refit_3pt", "mh_modes_to_hypotheses", "mh_neighbourhood", "mh_alpha_expansion", "mh_process", "mh_get_energy",
-    "mh_get_iterations", "mh_get_stage_ms", "mh_diag_fp32_peak", "mh_diag_mma_tf32_peak", "mh_diag_set_fused_variant", "mh_diag_set_fast_config", "mh_diag_get_fast_config", "mh_diag_set_dense_variant", "mh_diag_get_alternating_ms",
+    "mh_get_iterations", "mh_get_stage_ms", "mh_diag_fp32_peak", "mh_diag_mma_tf32_peak", "mh_diag_set_fused_variant", "mh_diag_set_fast_config", "mh_diag_get_fast_config", "mh_diag_set_dense_variant", "mh_diag_get_alternating_ms", "mh_diag_set_neighbourhood_backend",
 ]
 
 
@@ -105,21 +105,27 @@ def _p(a, ct):
 
 
 # ---- host-only entry points (no GPU needed) --------------------------------------------------------------------------
-def neighbourhood(pts, radius, max_neighbours=31):
-    """mh_neighbourhood: 4-D neighbourhood replacing FlannBasedMatcher::radiusMatch (MultiH.cpp:231-253)."""
+def neighbourhood(pts, radius, max_neighbours=31, ctx=None, backend=0):
+    """mh_neighbourhood: 4-D neighbourhood replacing FlannBasedMatcher::radiusMatch (MultiH.cpp:231-253).  ctx = None: host
+    search; with a Context: backend 0 = auto, 1 = host, 2 = device (K5)."""
     pts = _np(pts, np.float64)
     N = pts.shape[0]
-    offsets = np.zeros(N + 1, dtype=np.int64)
-    total = C.c_int64(0)
-    st = lib().mh_neighbourhood(None, _p(pts, C.c_double), N, C.c_double(radius), int(max_neighbours),
-                                _p(offsets, C.c_int64), None, C.byref(total))
-    if st:
-        raise MHError(st, "mh_neighbourhood")
-    adj = np.zeros(max(total.value, 1), dtype=np.int32)
-    st = lib().mh_neighbourhood(None, _p(pts, C.c_double), N, C.c_double(radius), int(max_neighbours),
-                                _p(offsets, C.c_int64), _p(adj, C.c_int32), C.byref(total))
-    if st:
-        raise MHError(st, "mh_neighbourhood")
+    h = None if ctx is None else ctx._h
+    lib().mh_diag_set_neighbourhood_backend(None, int(backend))
+    try:
+        offsets = np.zeros(N + 1, dtype=np.int64)
+        total = C.c_int64(0)
+        st = lib().mh_neighbourhood(h, _p(pts, C.c_double), N, C.c_double(radius), int(max_neighbours),
+                                    _p(offsets, C.c_int64), None, C.byref(total))
+        if st:
+            raise MHError(st, "mh_neighbourhood")
+        adj = np.zeros(max(total.value, 1), dtype=np.int32)
+        st = lib().mh_neighbourhood(h, _p(pts, C.c_double), N, C.c_double(radius), int(max_neighbours),
+                                    _p(offsets, C.c_int64), _p(adj, C.c_int32), C.byref(total))
+        if st:
+            raise MHError(st, "mh_neighbourhood")
+    finally:
+        lib().mh_diag_set_neighbourhood_backend(None, 0)
     return offsets, adj[: total.value]
 
 

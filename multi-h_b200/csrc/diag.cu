@@ -68,13 +68,15 @@ extern "C" mh_status mh_diag_fp32_peak(mh_ctx* ctx, int32_t variant, int32_t ite
   return MH_OK;
 }
 
-namespace mh { extern int g_fused_variant; extern int g_fast_config; extern int g_dense_variant; }
+namespace mh { extern int g_fused_variant; extern int g_fast_config; extern int g_dense_variant; extern int g_nb_backend; }
 // 1 = packed FFMA2 inner loop (default), 0 = scalar FFMA (kept for A/B evidence)
 extern "C" mh_status mh_diag_set_fused_variant(mh_ctx*, int32_t v) { mh::g_fused_variant = v ? 1 : 0; return MH_OK; }
 // launch shape of the K2 fast path (threads/CTA x CTAs/SM): 0 = 256x3, 1 = 256x2, 2 = 256x4, 3 = 128x5, 4 = 128x6, 5 = 128x7 (default), 6 = 128x4
 extern "C" mh_status mh_diag_set_fast_config(mh_ctx*, int32_t v) { mh::g_fast_config = v; return MH_OK; }
 extern "C" int32_t mh_diag_get_fast_config(mh_ctx*) { return mh::g_fast_config; }
 extern "C" mh_status mh_diag_set_dense_variant(mh_ctx*, int32_t v) { mh::g_dense_variant = v; return MH_OK; }
+// mh_neighbourhood backend: 0 = auto, 1 = host grid search, 2 = K5 on the device (needs a context)
+extern "C" mh_status mh_diag_set_neighbourhood_backend(mh_ctx*, int32_t v) { mh::g_nb_backend = v; return MH_OK; }
 
 // legacy-path tensor probe: mma.sync.m16n8k8 TF32 issue rate (used to judge whether the 3x3 homography product of K2
 // could move off the FP32 pipe); returns dense TFLOP/s (2*16*8*8 flop per warp instruction)

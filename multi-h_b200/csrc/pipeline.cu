@@ -24,6 +24,9 @@ namespace mh {
 mh_status alpha_expansion(const int32_t* cost, int N, int L, int potts, const int64_t* offsets, const int32_t* adj,
                           const int32_t* init, int max_cycles, int32_t* lab, int64_t* energy_out);
 int64_t radius_neighbourhood(const double* pts, int N, double radius, int max_neighbours, int64_t* offsets, int32_t* adj);
+mh_status neighbourhood_device(mh_ctx* ctx, const double* pts, int N, double radius, int max_neighbours, int64_t* offsets,
+                               int32_t* adj, int64_t* total_out);   // k5_neighbourhood.cu
+int g_nb_backend = 0;   // 0 = auto (device when there is a context and the list length is bounded), 1 = host, 2 = device
 }  // namespace mh
 
 using namespace mh;
@@ -57,8 +60,13 @@ extern "C" {
 
 mh_status mh_neighbourhood(mh_ctx* ctx, const double* pts, int32_t N, double radius, int32_t max_neighbours,
                            int64_t* offsets, int32_t* adj, int64_t* total_out) {
-  // host-only: ctx may be NULL
+  // ctx may be NULL: host search.  With a context and a bounded list length (the reference's effective 31) the search runs on
+  // the GPU (K5, k5_neighbourhood.cu) — same set, bit for bit.
   if (N < 0 || (N && !pts) || !(radius >= 0)) return ctx ? fail(ctx, MH_EINVAL, "mh_neighbourhood: bad arguments") : MH_EINVAL;
+  const bool can_device = ctx && max_neighbours >= 1 && max_neighbours <= 64;
+  if (g_nb_backend == 2 && !can_device) return ctx ? fail(ctx, MH_EINVAL, "mh_neighbourhood: device backend needs a context and 1 <= max_neighbours <= 64") : MH_EINVAL;
+  if (can_device && (g_nb_backend == 2 || (g_nb_backend == 0 && N >= 256)))
+    return neighbourhood_device(ctx, pts, N, radius, max_neighbours, offsets, adj, total_out);
   const int64_t t = radius_neighbourhood(pts, N, radius, max_neighbours, offsets, adj);
   if (total_out) *total_out = t;
   return MH_OK;

@@ -334,6 +334,26 @@ def test_k3_meanshift_cycling_trajectory_is_capped_like_the_oracle(mh, orc):
     assert (asg.cpu().numpy() == ao).mean() >= 0.999
 
 
+def test_k5_neighbourhood_device_equals_host(mh, orc):
+    """K5: the GPU grid search returns the host search's CSR bit for bit — which the CPU tests pin on the
+    oracle — for sparse and dense radii, k = 1 .. 64, duplicated points (ties by index), tiny inputs, and at 100k points."""
+    ctx = mh.Context()
+    sc = mh.scenes.make_scene(1500, 4, seed=21)
+    dup = np.concatenate([sc.pts, sc.pts[:200], sc.pts[:50]])           # exact duplicates: d2 = 0 ties, resolved by index
+    for pts in (sc.pts, dup, sc.pts[:3], sc.pts[:40]):
+        for radius, k in ((0.0, 31), (12.5, 5), (60.0, 31), (200.0, 31), (200.0, 1), (200.0, 64), (1e4, 31)):
+            o1, a1 = mh.capi.neighbourhood(pts, radius, k)                          # host
+            o2, a2 = mh.capi.neighbourhood(pts, radius, k, ctx=ctx, backend=2)      # device
+            assert np.array_equal(o1, o2) and np.array_equal(a1, a2), (len(pts), radius, k)
+    big = mh.scenes.make_scene(100_000, 20, seed=0xB200 + 2)
+    o1, a1 = mh.capi.neighbourhood(big.pts, 200.0, 31)
+    o2, a2 = mh.capi.neighbourhood(big.pts, 200.0, 31, ctx=ctx)                     # auto -> device
+    assert np.array_equal(o1, o2) and np.array_equal(a1, a2)
+    o3, a3 = orc.radius_neighbours(big.pts[:5000], 200.0, 31)
+    o4, a4 = mh.capi.neighbourhood(big.pts[:5000], 200.0, 31, ctx=ctx, backend=2)
+    assert np.array_equal(o3, o4) and np.array_equal(a3, a4)
+
+
 def _ari(a, b):
     """adjusted Rand index of two labelings (label ids may be permuted between runs)"""
     a = np.unique(a, return_inverse=True)[1]; b = np.unique(b, return_inverse=True)[1]
