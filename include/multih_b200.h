@@ -68,6 +68,8 @@ typedef struct mh_params {
   int32_t prefilter;        /* mh_process: 1 = run K0 first (MultiH.cpp:807-838: Hartley-Sturm correction, affine
                                consistency test, optimal affine) as Process() does after estimating F; dropped
                                correspondences get label -2.  0 (default) = inputs are already refined             */
+  int32_t compatibility_check; /* mh_process: 1 = finish with HomographyCompatibilityCheck (MultiH.cpp:78-86, 100-222) as
+                                  Process() does; 0 (default) = return the clusters of the alternating optimisation       */
 } mh_params;
 
 void mh_default_params(mh_params* p); /* main.cpp:55-59: 2.6 / 2.2 / 0.005 / 0.5 / 20 */
@@ -213,6 +215,26 @@ mh_status mh_alpha_expansion(mh_ctx* ctx, const int32_t* cost_host, int32_t N, i
  * -> host alpha-expansion) + refit (K4) } until convergence (MultiH.cpp:224-312).
  * labels_out: N, -1 = outlier (GetLabels, MultiH.h:62), -2 = dropped by the pre-filter (params.prefilter only); H_out: up to Kmax x 9 px (GetHomography, MultiH.h:69);
  * K_out = GetClusterNumber (MultiH.h:67). */
+/* HomographyCompatibilityCheck (MultiH.cpp:100-222): cross-validation of the clusters — 501 random three-point fits per
+ * cluster (GPU), median of the per-trial median transfer errors against thr_H^2 * 81/16; clusters that fail, and clusters
+ * with fewer than min_inliers members, are removed (their points become outliers, higher labels move down).  Serial draw
+ * order of the context's rand() restatement.  labels_host [N] and H_host [K][9] (pixel) are updated in place, *K_inout too;
+ * medians_out [K] optional (NaN = cluster not tested).  Needs mh_set_geometry (F). */
+mh_status mh_compatibility_check(mh_ctx* ctx, const double* pts_host, int32_t N, int32_t* labels_host, double* H_host,
+                                 int32_t* K_inout, double* medians_out);
+/* Its two host halves (no context; mh_compatibility_check = plan -> GPU order statistics -> decide):
+ * plan   replays the reference's sampling (rand() draws without replacement from an evolving point vector, MultiH.cpp:142-154,
+ *        183-194): per tested cluster (>= max(min_inliers, 4) members) its members [moff[k], moff[k+1]) in index order and
+ *        MH_COMPAT_TRIALS x 3 sampled correspondence indices; removed[c] = 1 for clusters below min_inliers.
+ * decide takes per (tested cluster, trial) 8 doubles — the sorted squared transfer errors of the n = members - 3 other members
+ *        at indices max(0, n/2 - 3) .. min(n - 1, n/2 + 1) (5 slots, +inf when absent) and the three largest (-inf when absent) —
+ *        replays the reference's per-trial "median" with its three stale buffer entries and the off-by-one even case
+ *        (MultiH.cpp:140, 177-178), takes the median over the trials, removes clusters above thr_H^2 * 81/16 and relabels. */
+#define MH_COMPAT_TRIALS 501 /* MAX(501, MIN(501, n choose 3)), MultiH.cpp:130 */
+mh_status mh_compat_plan(const int32_t* labels, int32_t N, int32_t K, int32_t min_inliers, uint32_t* rng_state, int32_t* tested,
+                         int32_t* T_out, int32_t* members, int32_t* moff, int32_t* samples, int32_t* removed);
+mh_status mh_compat_decide(const int32_t* tested, int32_t T, const int32_t* moff, const double* stats, double thr_homography,
+                           int32_t* removed, int32_t N, int32_t* labels, double* H, int32_t* K_inout, double* medians_out);
 mh_status mh_process(mh_ctx* ctx, const double* pts_host, const double* aff_host, const double F[9], int32_t N,
                      int32_t* labels_out, double* H_out, int32_t Kmax, int32_t* K_out);
 double mh_get_energy(const mh_ctx* ctx);        /* GetEnergy          (MultiH.h:74) */

@@ -26,7 +26,7 @@ SYMBOLS = [
     "mh_set_geometry", "mh_get_geometry", "mh_upload_correspondences", "mh_hypotheses_from_host",
     "mh_hypotheses_to_host", "mh_prefilter", "mh_prefilter_device", "mh_haf_hypotheses", "mh_data_cost_dense", "mh_residuals", "mh_data_cost_fused",
     "mh_inlier_stats", "mh_inliers_of_homography", "mh_features10", "mh_features6", "mh_set_rng_state", "mh_get_rng_state", "mh_meanshift", "mh_refit_haf",
-    "mh_refit_haf_accumulate", "mh_refit_haf_solve", "mh_labels_from_best", "mh_pack_inlier_counts", "mh_refit_3pt", "mh_modes_to_hypotheses", "mh_neighbourhood", "mh_alpha_expansion", "mh_process", "mh_get_energy",
+    "mh_refit_haf_accumulate", "mh_refit_haf_solve", "mh_labels_from_best", "mh_pack_inlier_counts", "mh_refit_3pt", "mh_modes_to_hypotheses", "mh_neighbourhood", "mh_alpha_expansion", "mh_compatibility_check", "mh_compat_plan", "mh_compat_decide", "mh_process", "mh_get_energy",
     "mh_get_iterations", "mh_get_stage_ms", "mh_diag_fp32_peak", "mh_diag_mma_tf32_peak", "mh_diag_set_fused_variant", "mh_diag_set_fast_config", "mh_diag_get_fast_config", "mh_diag_set_dense_variant", "mh_diag_get_alternating_ms", "mh_diag_set_neighbourhood_backend",
 ]
 
@@ -44,6 +44,7 @@ class Params(C.Structure):
         ("lambda_", C.c_double), ("min_inliers", C.c_int32), ("straightness", C.c_double),
         ("max_iterations", C.c_int32), ("convergence", C.c_double), ("meanshift_metric", C.c_int32),
         ("rng_seed", C.c_uint32), ("max_gc_cycles", C.c_int32), ("max_neighbours", C.c_int32), ("precise_pipeline", C.c_int32), ("prefilter", C.c_int32),
+        ("compatibility_check", C.c_int32),
     ]
 
 
@@ -393,6 +394,17 @@ class Context:
         self._check(lib().mh_process(self._h, _p(pts, C.c_double), _p(aff, C.c_double), _p(F, C.c_double), N,
                                      _p(labels, C.c_int32), _p(H, C.c_double), int(kmax), C.byref(K)))
         return labels, H[: K.value].copy(), int(K.value)
+
+    def compatibility_check(self, pts, labels, H):
+        """mh_compatibility_check (MultiH.cpp:100-222): returns (labels, H, medians) after the cross-validation filter."""
+        pts = _np(pts, np.float64)
+        lab = np.ascontiguousarray(labels, dtype=np.int32).copy()
+        Hc = np.ascontiguousarray(np.asarray(H, dtype=np.float64).reshape(-1, 9)).copy()
+        K = C.c_int32(Hc.shape[0])
+        med = np.full(max(Hc.shape[0], 1), np.nan)
+        self._check(lib().mh_compatibility_check(self._h, _p(pts, C.c_double), pts.shape[0], _p(lab, C.c_int32),
+                                                 _p(Hc, C.c_double), C.byref(K), _p(med, C.c_double)))
+        return lab, Hc[: K.value], med[: Hc.shape[0]]
 
     def fp32_peak(self, variant=1, iters=20000):
         tf = C.c_double(0); ms = C.c_double(0)

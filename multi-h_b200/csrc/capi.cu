@@ -153,6 +153,7 @@ void mh_default_params(mh_params* p) {
   p->max_neighbours = 31;    // FLANN default SearchParams: checks = 32 (query included)
   p->precise_pipeline = 1;
   p->prefilter = 0;
+  p->compatibility_check = 0;
 }
 
 mh_status mh_create(const mh_params* params, int device, mh_ctx** out) {

@@ -503,4 +503,110 @@ mh_status launch_modes_to_hyp(mh_ctx* ctx, const double* d_modes, int C, float* 
   return MH_OK;
 }
 
+// ---- HomographyCompatibilityCheck (MultiH.cpp:100-222), the data-parallel part ----------------------------------------
+// One CTA per (tested cluster, trial): thread 0 fits GetHomography3PT (no refinement, :157) to the trial's three sampled
+// members — the same device functions as modes_to_hyp_kernel, a general first point set — then all threads evaluate the squared
+// transfer error of the cluster's other members (:162-175) into shared memory, sort it (bitonic, FP64) and write the order
+// statistics the host needs to replay the reference's median with its three stale buffer entries (pipeline.cu): sorted values
+// [max(0, m-3) .. min(n-1, m+1)] around the median index m = n/2 (5 slots, +inf when absent) and the three largest (-inf when
+// absent).  The sampling itself — sequential rand() draws without replacement from an evolving point vector — is index
+// bookkeeping and stays on the host.
+constexpr int COMPAT_THREADS = 256;
+__global__ void __launch_bounds__(COMPAT_THREADS)
+compat_trial_kernel(const double* __restrict__ pts64, const int32_t* __restrict__ members, const int32_t* __restrict__ moff,
+                    const int32_t* __restrict__ samples /*[T][trials][3]*/, int trials, int P /*pow2 >= max n*/, HafGeom g,
+                    double* __restrict__ out /*[T][trials][8]*/) {
+  extern __shared__ double compat_sd[];
+  __shared__ double sH[9];
+  const int c = blockIdx.y, t = blockIdx.x, tid = threadIdx.x;
+  const int beg = moff[c], end = moff[c + 1], n = end - beg - 3;
+  const int32_t* sm = samples + ((size_t)c * trials + t) * 3;
+  const int s0 = sm[0], s1 = sm[1], s2 = sm[2];
+  if (tid == 0) {
+    double p1[3][2], p2[3][2];
+    const int si[3] = {s0, s1, s2};
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const double* q = pts64 + 4 * (size_t)si[k];
+      p1[k][0] = q[0]; p1[k][1] = q[1]; p2[k][0] = q[2]; p2[k][1] = q[3];
+    }
+    Norm2 nm;   // NormalizePoints (3PTcb.h:146-197) on the three pairs
+    nm.mx1 = (p1[0][0] + p1[1][0] + p1[2][0]) / 3.0; nm.my1 = (p1[0][1] + p1[1][1] + p1[2][1]) / 3.0;
+    nm.mx2 = (p2[0][0] + p2[1][0] + p2[2][0]) / 3.0; nm.my2 = (p2[0][1] + p2[1][1] + p2[2][1]) / 3.0;
+    double d1 = 0, d2 = 0;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      d1 += sqrt((p1[k][0] - nm.mx1) * (p1[k][0] - nm.mx1) + (p1[k][1] - nm.my1) * (p1[k][1] - nm.my1));
+      d2 += sqrt((p2[k][0] - nm.mx2) * (p2[k][0] - nm.mx2) + (p2[k][1] - nm.my2) * (p2[k][1] - nm.my2));
+    }
+    nm.s1 = sqrt(2.0) / (d1 / 3.0);
+    nm.s2 = sqrt(2.0) / (d2 / 3.0);
+    double Fn[9], ex, ey;
+    normalised_F_and_epipole(g, nm, Fn, ex, ey);
+    double Nq[6] = {0, 0, 0, 0, 0, 0}, r[3] = {0, 0, 0};
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+      rows_3pt((p1[k][0] - nm.mx1) * nm.s1, (p1[k][1] - nm.my1) * nm.s1, (p2[k][0] - nm.mx2) * nm.s2,
+               (p2[k][1] - nm.my2) * nm.s2, ex, ey, Fn, Nq, r);
+    double h3[3], H[9];
+    pinv_normal3(Nq, r, h3);
+    __align__(16) float unused[12];
+    assemble_3pt_and_store(h3, Fn, ex, ey, nm, g, unused, H);
+#pragma unroll
+    for (int k = 0; k < 9; ++k) sH[k] = H[k];
+  }
+  __syncthreads();
+  double h[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) h[k] = sH[k];
+  const double inf = __longlong_as_double(0x7ff0000000000000LL);
+  // members are listed in ascending index order, so a member's slot among the non-sampled ones is its rank minus the number
+  // of sampled indices below it
+  for (int j = beg + tid; j < end; j += COMPAT_THREADS) {
+    const int idx = members[j];
+    if (idx == s0 || idx == s1 || idx == s2) continue;
+    const int pos = (j - beg) - (s0 < idx) - (s1 < idx) - (s2 < idx);
+    const double* q = pts64 + 4 * (size_t)idx;
+    const double s = h[6] * q[0] + h[7] * q[1] + h[8];
+    const double x1 = (h[0] * q[0] + h[1] * q[1] + h[2]) / s, y1 = (h[3] * q[0] + h[4] * q[1] + h[5]) / s;
+    const double dx = q[2] - x1, dy = q[3] - y1;
+    double d = dx * dx + dy * dy;
+    if (!(d == d)) d = inf;   // NaN (a member on the homography's horizon line): sorts last
+    compat_sd[pos] = d;
+  }
+  for (int j = n + tid; j < P; j += COMPAT_THREADS) compat_sd[j] = inf;
+  __syncthreads();
+  for (int k = 2; k <= P; k <<= 1)
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = tid; i < P; i += COMPAT_THREADS) {
+        const int l = i ^ j;
+        if (l > i) {
+          const double a = compat_sd[i], b = compat_sd[l];
+          if ((a > b) == ((i & k) == 0)) { compat_sd[i] = b; compat_sd[l] = a; }
+        }
+      }
+      __syncthreads();
+    }
+  if (tid == 0) {
+    double* o = out + ((size_t)c * trials + t) * 8;
+    const int m = n / 2, lo = max(0, m - 3), hi = min(n - 1, m + 1);
+    for (int k = 0; k < 5; ++k) o[k] = (lo + k <= hi) ? compat_sd[lo + k] : inf;
+    for (int k = 0; k < 3; ++k) o[5 + k] = (n - 1 - k >= 0) ? compat_sd[n - 1 - k] : -inf;
+  }
+}
+
+mh_status launch_compat_trials(mh_ctx* ctx, const double* d_pts64, const int32_t* d_members, const int32_t* d_moff,
+                               const int32_t* d_samples, int T, int trials, int max_n, double* d_out) {
+  if (T <= 0) return MH_OK;
+  int P = 2;
+  while (P < max_n) P <<= 1;
+  const size_t smem = (size_t)P * sizeof(double);
+  if (smem > 200 * 1024) return fail(ctx, MH_EINVAL, "mh_compatibility_check: a cluster has more than 25600 members");
+  MH_CUDA(ctx, cudaFuncSetAttribute(compat_trial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  compat_trial_kernel<<<dim3((unsigned)trials, (unsigned)T), COMPAT_THREADS, smem, ctx->stream>>>(
+      d_pts64, d_members, d_moff, d_samples, trials, P, haf_geom(ctx), d_out);
+  MH_LAUNCHED(ctx, "compat_trial_kernel");
+  return MH_OK;
+}
+
 }  // namespace mh

@@ -26,6 +26,8 @@ mh_status alpha_expansion(const int32_t* cost, int N, int L, int potts, const in
 int64_t radius_neighbourhood(const double* pts, int N, double radius, int max_neighbours, int64_t* offsets, int32_t* adj);
 mh_status neighbourhood_device(mh_ctx* ctx, const double* pts, int N, double radius, int max_neighbours, int64_t* offsets,
                                int32_t* adj, int64_t* total_out);   // k5_neighbourhood.cu
+mh_status launch_compat_trials(mh_ctx* ctx, const double* d_pts64, const int32_t* d_members, const int32_t* d_moff,
+                               const int32_t* d_samples, int T, int trials, int max_n, double* d_out);   // k4_refit.cu
 int g_nb_backend = 0;   // 0 = auto (device when there is a context and the list length is bounded), 1 = host, 2 = device
 }  // namespace mh
 
@@ -79,6 +81,143 @@ mh_status mh_alpha_expansion(mh_ctx* ctx, const int32_t* cost, int32_t N, int32_
   const mh_status st = alpha_expansion(cost, N, L, potts, offsets, adj, init, max_cycles, labels, energy);
   if (st != MH_OK && ctx) ctx->err = "mh_alpha_expansion: invalid labels or sizes";
   return st;
+}
+
+// HomographyCompatibilityCheck (MultiH.cpp:100-222) in three parts.
+//   mh_compat_plan   (host)  the sampling: rand() draws without replacement from a point vector whose order evolves from trial
+//                            to trial (:142-154, :183-194) — sequential index bookkeeping, replayed exactly;
+//   compat_trial_kernel (GPU) the 501 x clusters three-point fits, transfer errors and their order statistics;
+//   mh_compat_decide (host)  the reference's "median" per trial INCLUDING the three stale entries of its distance buffer
+//                            (see oracle/multih_oracle.cpp orc_compatibility_check), median over the trials, the decision and
+//                            the relabelling (:200-230).
+// The two host halves take plain arrays (no context) so that the CPU tests can drive them with oracle-computed statistics.
+mh_status mh_compat_plan(const int32_t* labels, int32_t N, int32_t K, int32_t min_inliers, uint32_t* rng_state,
+                         int32_t* tested /*[K]*/, int32_t* T_out, int32_t* members /*[N]*/, int32_t* moff /*[K+1]*/,
+                         int32_t* samples /*[K][501][3]*/, int32_t* removed /*[K]*/) {
+  if (!labels || !rng_state || !tested || !T_out || !members || !moff || !samples || !removed || N < 0 || K < 0) return MH_EINVAL;
+  const int trials = MH_COMPAT_TRIALS;
+  uint32_t hold = *rng_state;
+  auto msvc_rand = [&]() { hold = hold * 214013u + 2531011u; return (int)((hold >> 16) & 0x7fff); };
+  std::vector<std::vector<int32_t>> per(K);                     // members in index order (MultiH.cpp:106-114)
+  for (int i = 0; i < N; ++i)
+    if (labels[i] > -1 && labels[i] < K) per[labels[i]].push_back(i);
+  int T = 0;
+  size_t nm = 0, ns = 0;
+  moff[0] = 0;
+  for (int c = 0; c < K; ++c) {
+    const int n = (int)per[c].size();
+    removed[c] = 0;
+    if (n >= std::max(min_inliers, 4)) {
+      tested[T] = c;
+      std::memcpy(members + nm, per[c].data(), sizeof(int32_t) * (size_t)n);
+      nm += (size_t)n;
+      moff[++T] = (int32_t)nm;
+      std::vector<int32_t> v = per[c];                          // the evolving point vector, as indices
+      for (int t = 0; t < trials; ++t) {
+        int32_t pick[3];
+        for (int j = 0; j < 3; ++j) {
+          const int idx = (int)((double)(v.size() - 1) * ((double)msvc_rand() / 32767.0));   // MultiH.cpp:145
+          pick[j] = v[idx];
+          v.erase(v.begin() + idx);
+        }
+        samples[ns++] = pick[0]; samples[ns++] = pick[1]; samples[ns++] = pick[2];
+        v.resize(n);
+        for (int j = 0; j < 3; ++j) v[n - j - 1] = pick[j];     // MultiH.cpp:183-194
+      }
+    } else if (n < min_inliers) {
+      removed[c] = 1;                                           // MultiH.cpp:207-208
+    }
+  }
+  *T_out = T;
+  *rng_state = hold;
+  return MH_OK;
+}
+
+mh_status mh_compat_decide(const int32_t* tested, int32_t T, const int32_t* moff, const double* stats /*[T][501][8]*/,
+                           double thr_homography, int32_t* removed /*[K] in/out*/, int32_t N, int32_t* labels, double* H,
+                           int32_t* K_inout, double* medians_out /*[K] or NULL*/) {
+  if (!K_inout || (T > 0 && (!tested || !moff || !stats)) || !removed || (N > 0 && !labels) || !H) return MH_EINVAL;
+  const int trials = MH_COMPAT_TRIALS, K = *K_inout;
+  const double limit = thr_homography * thr_homography * 81.0 / 16.0;
+  if (medians_out)
+    for (int c = 0; c < K; ++c) medians_out[c] = std::nan("");
+  std::vector<double> distances(trials);
+  for (int k = 0; k < T; ++k) {
+    const int c = tested[k], n = moff[k + 1] - moff[k] - 3, m = n / 2, lo = std::max(0, m - 3);
+    double stale[3] = {0.0, 0.0, 0.0};                          // the buffer starts zeroed (MultiH.cpp:140)
+    // q-th smallest of (the trial's n errors) U (3 stale entries), from the window [lo, min(n-1, m+1)] of the sorted errors:
+    // the lo entries below the window all rank below q, so it is the (q - lo)-th smallest of window U stale
+    auto kth = [&](const double* w, int q) {
+      double u[8];
+      int cnt = 0;
+      for (int i = 0; i < 5; ++i)
+        if (lo + i <= std::min(n - 1, q)) u[cnt++] = w[i];
+      for (int i = 0; i < 3; ++i) u[cnt++] = stale[i];
+      std::sort(u, u + cnt);
+      return u[q - lo];
+    };
+    for (int t = 0; t < trials; ++t) {
+      const double* w = stats + 8 * ((size_t)k * trials + t);
+      distances[t] = n % 2 ? kth(w, m) : 0.5 * (kth(w, m) + kth(w, m + 1));   // MultiH.cpp:178
+      double u[6] = {w[5], w[6], w[7], stale[0], stale[1], stale[2]};         // next trial's stale entries: the buffer's top 3
+      std::sort(u, u + 6);
+      stale[0] = u[3]; stale[1] = u[4]; stale[2] = u[5];
+    }
+    std::sort(distances.begin(), distances.end());
+    const double median = distances[trials / 2];                // trials is odd (MultiH.cpp:200)
+    if (medians_out) medians_out[c] = median;
+    removed[c] = median > limit;                                // MultiH.cpp:202
+  }
+  int Kn = K;
+  for (int c = K - 1; c >= 0; --c)                              // MultiH.cpp:216-230
+    if (removed[c]) {
+      for (int j = 0; j < N; ++j) {
+        if (labels[j] == c) labels[j] = -1;
+        else if (labels[j] > c) --labels[j];
+      }
+      for (int k = c; k + 1 < Kn; ++k) std::memcpy(H + 9 * (size_t)k, H + 9 * (size_t)(k + 1), sizeof(double) * 9);
+      --Kn;
+    }
+  *K_inout = Kn;
+  return MH_OK;
+}
+
+mh_status mh_compatibility_check(mh_ctx* ctx, const double* pts, int32_t N, int32_t* labels, double* H, int32_t* K_inout,
+                                 double* medians_out) {
+  if (!ctx) return MH_EINVAL;
+  if (!pts || !labels || !H || !K_inout || N < 0) return fail(ctx, MH_EINVAL, "mh_compatibility_check: null argument");
+  if (!ctx->have_geom) return fail(ctx, MH_EINVAL, "mh_compatibility_check: call mh_set_geometry first");
+  const int K = *K_inout;
+  if (K <= 0) return MH_OK;
+  const int trials = MH_COMPAT_TRIALS;
+  std::vector<int32_t> tested(K), members((size_t)std::max(N, 1)), moff((size_t)K + 1), samples((size_t)K * trials * 3), removed(K);
+  int32_t T = 0;
+  if (mh_compat_plan(labels, N, K, ctx->params.min_inliers, &ctx->rng_state, tested.data(), &T, members.data(), moff.data(),
+                     samples.data(), removed.data()) != MH_OK)
+    return fail(ctx, MH_EINVAL, "mh_compatibility_check: bad labels");
+  std::vector<double> stat(8 * (size_t)T * trials);
+  if (T > 0) {
+    int max_n = 0;
+    for (int k = 0; k < T; ++k) max_n = std::max(max_n, moff[k + 1] - moff[k] - 3);
+    uint64_t off = 0;
+    auto take = [&](uint64_t bytes) { uint64_t o = off; off = (off + bytes + 255) & ~uint64_t(255); return o; };
+    const uint64_t o_pts = take(sizeof(double) * 4 * (uint64_t)N), o_mem = take(sizeof(int32_t) * (uint64_t)moff[T]),
+                   o_off = take(sizeof(int32_t) * ((uint64_t)T + 1)), o_smp = take(sizeof(int32_t) * 3 * (uint64_t)T * trials),
+                   o_out = take(sizeof(double) * 8 * (uint64_t)T * trials);
+    MH_TRY(ensure_staging(ctx, off));
+    char* base = (char*)ctx->staging;
+    MH_TRY(mh_memcpy_h2d(ctx, base + o_pts, pts, sizeof(double) * 4 * (size_t)N));
+    MH_TRY(mh_memcpy_h2d(ctx, base + o_mem, members.data(), sizeof(int32_t) * (size_t)moff[T]));
+    MH_TRY(mh_memcpy_h2d(ctx, base + o_off, moff.data(), sizeof(int32_t) * ((size_t)T + 1)));
+    MH_TRY(mh_memcpy_h2d(ctx, base + o_smp, samples.data(), sizeof(int32_t) * 3 * (size_t)T * trials));
+    MH_TRY(launch_compat_trials(ctx, (const double*)(base + o_pts), (const int32_t*)(base + o_mem), (const int32_t*)(base + o_off),
+                                (const int32_t*)(base + o_smp), T, trials, max_n, (double*)(base + o_out)));
+    MH_TRY(mh_memcpy_d2h(ctx, stat.data(), base + o_out, sizeof(double) * stat.size()));
+  }
+  if (mh_compat_decide(tested.data(), T, moff.data(), stat.data(), ctx->params.thr_homography, removed.data(), N, labels, H,
+                       K_inout, medians_out) != MH_OK)
+    return fail(ctx, MH_EINVAL, "mh_compatibility_check: bad arguments");
+  return MH_OK;
 }
 
 mh_status mh_process(mh_ctx* ctx, const double* pts, const double* aff, const double F[9], int32_t N, int32_t* labels_out,
@@ -328,6 +467,17 @@ mh_status mh_process(mh_ctx* ctx, const double* pts, const double* aff, const do
   ctx->iterations = iteration_number - 1;  // MultiH.cpp:311
   ctx->stage_ms[3] = now_ms() - t0;
 
+  // pixel-space homographies of the surviving clusters
+  std::vector<double> Hpix(9 * (size_t)std::max(K, 1));
+  for (int k = 0; k < K; ++k) {
+    if (precise) std::memcpy(Hpix.data() + 9 * (size_t)k, hyp64.data() + 9 * (size_t)k, sizeof(double) * 9);
+    else mh::hyp_norm_to_px(ctx, hyp.data() + 12 * (size_t)k, Hpix.data() + 9 * (size_t)k, false);
+  }
+  if (P.compatibility_check && K > 1) {  // MultiH.cpp:78-86 (HandleDegenerateCase, :88-94, stays with the caller)
+    int32_t Kc = K;
+    MH_TRY(mh_compatibility_check(ctx, pts, N, labeling.data(), Hpix.data(), &Kc, nullptr));
+    K = Kc;
+  }
   if (P.prefilter) {  // labels of the survivors in input order; -2 marks correspondences the pre-filter dropped
     int j = 0;
     for (int i = 0; i < N_in; ++i) labels_out[i] = keepmask[i] ? labeling[j++] : -2;
@@ -335,11 +485,7 @@ mh_status mh_process(mh_ctx* ctx, const double* pts, const double* aff, const do
     std::memcpy(labels_out, labeling.data(), sizeof(int32_t) * (size_t)N);
   }
   *K_out = K;
-  if (H_out)
-    for (int k = 0; k < std::min(K, (int)Kmax); ++k) {
-      if (precise) std::memcpy(H_out + 9 * (size_t)k, hyp64.data() + 9 * (size_t)k, sizeof(double) * 9);
-      else mh::hyp_norm_to_px(ctx, hyp.data() + 12 * (size_t)k, H_out + 9 * (size_t)k, false);
-    }
+  if (H_out) std::memcpy(H_out, Hpix.data(), sizeof(double) * 9 * (size_t)std::min(K, (int)Kmax));
   ctx->stage_ms[4] = now_ms() - t_start;
   return MH_OK;
 }

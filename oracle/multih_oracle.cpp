@@ -29,6 +29,7 @@
 // threshold 2*DBL_EPSILON*sum(w)), cv::Mat::inv() on 3x3.
 // ============================================================================
 #include <algorithm>
+#include <array>
 #include <atomic>
 #include <cfloat>
 #include <cmath>
@@ -462,6 +463,87 @@ void orc_cluster_3pt(const double* pts, const int* offsets, const int* members, 
 void orc_mode_to_homography(const double* mode6, const double* F, double* H) {
   const double p1[6] = {0, 0, 1, 0, 0, 1};
   orc_homography_3pt(p1, mode6, 3, F, H);
+}
+
+// ---------------------------------------------------------------------------
+// Post-processing oracle.  MultiH::HomographyCompatibilityCheck (MH.cpp:100-222): a cross-validation filter on the
+// clusters the alternating optimisation returned.  Per cluster with N >= max(min_inliers, 4) members, 501 trials
+// (MH.cpp:130: MAX(501, MIN(501, .)) == 501): draw 3 members WITHOUT replacement from the cluster's point vector
+// (idx = (size-1) * rand()/RAND_MAX truncated, then erase: MH.cpp:142-154), fit GetHomography3PT without refinement
+// (:157), take the "median" squared transfer error of the remaining N-3 members (:162-181), put the three back at the
+// END of the vector in reverse draw order (:183-194).  The cluster is removed when the median over the trials exceeds
+// thr^2 * 81/16 (:200-203), or when it has fewer than min_inliers members (:207-208).  Removed clusters' points become
+// outliers and the higher labels move down (:216-230).
+// Reproduced as written, including
+//  * the distance buffer of size N of which only the first N-3 entries are rewritten per trial while ALL N are sorted
+//    (:140, :177): three stale values — the three largest of the previous trial's sorted buffer, zeros in the first
+//    trial — take part in every "median";
+//  * the even-length median 0.5 (d[n/2] + d[n/2+1]) (:178, :200; off by one);
+//  * rand() = the injected MSVC generator, clusters visited in index order (the reference's parallel_for makes the
+//    draw order nondeterministic; this is its serial order, USE_CONCURRENCY 0).
+// labels: in/out (N, -1 = outlier); H: in/out (K x 9, compacted); returns the new K; medians[K_in] (NaN = not tested),
+// removed[K_in].
+// ---------------------------------------------------------------------------
+int orc_compatibility_check(const double* pts, int64_t N, int32_t* labels, double* H, int K, const double* F, double thr,
+                            int min_inliers, uint32_t* rng_state, double* medians, int32_t* removed) {
+  uint32_t hold = rng_state ? *rng_state : 1u;
+  auto msvc_rand = [&]() { hold = hold * 214013u + 2531011u; return (int)((hold >> 16) & 0x7fff); };
+  const double limit = thr * thr * 81.0 / 16.0;
+  std::vector<std::vector<std::array<double, 4>>> per(K);
+  for (int64_t i = 0; i < N; ++i)
+    if (labels[i] > -1 && labels[i] < K) per[labels[i]].push_back({pts[4 * i], pts[4 * i + 1], pts[4 * i + 2], pts[4 * i + 3]});
+  std::vector<char> rem(K, 0);
+  const int trials = 501;
+  for (int c = 0; c < K; ++c) {
+    std::vector<std::array<double, 4>>& v = per[c];
+    const int n = (int)v.size();
+    if (medians) medians[c] = std::nan("");
+    if (n >= std::max(min_inliers, 4)) {
+      std::vector<double> dist(n, 0.0), distances(trials);
+      for (int t = 0; t < trials; ++t) {
+        double p1[6], p2[6];
+        std::array<double, 4> mss[3];
+        for (int j = 0; j < 3; ++j) {
+          const int idx = (int)((double)(v.size() - 1) * ((double)msvc_rand() / 32767.0));
+          mss[j] = v[idx];
+          p1[2 * j] = v[idx][0]; p1[2 * j + 1] = v[idx][1]; p2[2 * j] = v[idx][2]; p2[2 * j + 1] = v[idx][3];
+          v.erase(v.begin() + idx);
+        }
+        double h[9];
+        orc_homography_3pt(p1, p2, 3, F, h);
+        for (size_t j = 0; j < v.size(); ++j) {
+          const double s = h[6] * v[j][0] + h[7] * v[j][1] + h[8];
+          const double x1 = (h[0] * v[j][0] + h[1] * v[j][1] + h[2]) / s, y1 = (h[3] * v[j][0] + h[4] * v[j][1] + h[5]) / s;
+          const double dx = v[j][2] - x1, dy = v[j][3] - y1;
+          dist[j] = dx * dx + dy * dy;
+        }
+        std::sort(dist.begin(), dist.end());   // all n entries: the last three are stale
+        const size_t m = v.size();
+        distances[t] = m % 2 ? dist[m / 2] : 0.5 * (dist[m / 2] + dist[m / 2 + 1]);
+        v.resize(n);
+        for (int j = 0; j < 3; ++j) v[n - j - 1] = mss[j];
+      }
+      std::sort(distances.begin(), distances.end());
+      const double median = trials % 2 ? distances[trials / 2] : 0.5 * (distances[trials / 2] + distances[trials / 2 + 1]);
+      if (medians) medians[c] = median;
+      rem[c] = median > limit;
+    } else if (n < min_inliers) {
+      rem[c] = 1;
+    }
+    if (removed) removed[c] = rem[c];
+  }
+  int Kn = K;
+  for (int c = K - 1; c >= 0; --c)
+    if (rem[c]) {
+      for (int64_t j = 0; j < N; ++j) {
+        if (labels[j] == c) labels[j] = -1;
+        else if (labels[j] > c) --labels[j];
+      }
+      for (int k = c; k + 1 < Kn; ++k) std::memcpy(H + 9 * (size_t)k, H + 9 * (size_t)(k + 1), sizeof(double) * 9);
+      --Kn;
+    }
+  if (rng_state) *rng_state = hold;
+  return Kn;
 }
 
 // ---------------------------------------------------------------------------

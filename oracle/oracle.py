@@ -162,6 +162,24 @@ def cluster_3pt(pts, offsets, members, F):
     return H, keep.astype(bool)
 
 
+def compatibility_check(pts, labels, H, F, thr=2.2, min_inliers=20, rng_state=1):
+    """MultiH::HomographyCompatibilityCheck (MultiH.cpp:100-222), serial draw order.  Returns (labels, H, medians, removed,
+    rng_state); medians are NaN for clusters too small to be tested."""
+    pts, pp = _d(pts)
+    lab = np.ascontiguousarray(labels, dtype=np.int32).copy()
+    Hc = np.ascontiguousarray(np.asarray(H, dtype=np.float64).reshape(-1, 9)).copy()
+    K = Hc.shape[0]
+    F, pF = _d(F)
+    med = np.full(max(K, 1), np.nan)
+    rem = np.zeros(max(K, 1), dtype=np.int32)
+    st = C.c_uint32(rng_state)
+    f = lib().orc_compatibility_check
+    f.restype = C.c_int
+    Kn = f(pp, C.c_int64(len(pts)), lab.ctypes.data_as(c_ip), Hc.ctypes.data_as(c_dp), K, pF, C.c_double(thr),
+           int(min_inliers), C.byref(st), med.ctypes.data_as(c_dp), rem.ctypes.data_as(c_ip))
+    return lab, Hc[:Kn], med[:K], rem[:K].astype(bool), int(st.value)
+
+
 def mode_to_homography(mode6, F):
     m, pm = _d(mode6)
     F, pF = _d(F)

@@ -16,7 +16,8 @@ def _csr(assign, C):
 
 
 def oracle_process(pts, aff, F, thr=2.2, locality=0.005, lam=0.5, straightness=0.005, max_iterations=500,
-                   convergence=1e-5, max_gc_cycles=1000, rng_state=1, max_neighbours=31, prefilter=False, use_ref_gco=True, expansion=None, trace=None):
+                   convergence=1e-5, max_gc_cycles=1000, rng_state=1, max_neighbours=31, prefilter=False, use_ref_gco=True, expansion=None, trace=None,
+                   compatibility_check=False, min_inliers=20):
     if prefilter:                                                            # MultiH.cpp:807-838
         pts, aff, keepmask = orc.prefilter(pts, aff, F)
     N = len(pts)
@@ -66,6 +67,8 @@ def oracle_process(pts, aff, F, thr=2.2, locality=0.005, lam=0.5, straightness=0
             energy_final = energy
             break
         last_energy = energy
+    if compatibility_check and len(hyp) > 1:                                  # MultiH.cpp:78-86, 100-222
+        labeling, hyp, _, _, rng_state = orc.compatibility_check(pts, labeling, hyp, F, thr, min_inliers, rng_state)
     if prefilter:
         full = np.full(len(keepmask), -2, dtype=np.int32)
         full[keepmask] = labeling

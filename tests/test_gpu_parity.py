@@ -354,6 +354,37 @@ def test_k5_neighbourhood_device_equals_host(mh, orc):
     assert np.array_equal(o3, o4) and np.array_equal(a3, a4)
 
 
+def test_compatibility_check_vs_oracle(mh, orc):
+    """HomographyCompatibilityCheck: mh_compatibility_check (host sampling replay + compat_trial_kernel +
+    host median replay) against the oracle's line-by-line restatement: same clusters removed, same labels, same rand()
+    consumption, medians to 1e-6 (GPU 3-point fits vs the oracle's)."""
+    sc = mh.scenes.make_scene(3000, 5, seed=3)
+    lab = sc.gt.astype(np.int32).copy()
+    out_idx = np.where(lab < 0)[0]
+    lab[out_idx[:60]] = 5                       # a cluster made of outliers: must go
+    lab[out_idx[60:67]] = 6                     # a 7-member cluster: below min_inliers = 20 / tested with an even-length median at 4
+    H = np.concatenate([sc.planes, sc.planes[:2]])
+    for min_inl, seed in ((20, 1), (4, 77)):
+        ctx = mh.Context(mh.capi.default_params(min_inliers=min_inl))
+        ctx.set_geometry(sc.F, sc.pts)
+        ctx.rng_state = seed
+        l, Hn, med = ctx.compatibility_check(sc.pts, lab, H)
+        l_o, H_o, med_o, rem_o, rng_o = orc.compatibility_check(sc.pts, lab, H, sc.F, thr=2.2, min_inliers=min_inl, rng_state=seed)
+        assert ctx.rng_state == rng_o
+        assert np.array_equal(l, l_o) and np.array_equal(Hn, H_o)
+        ok = ~np.isnan(med_o)
+        assert np.array_equal(np.isnan(med), np.isnan(med_o)) and np.allclose(med[ok], med_o[ok], rtol=1e-6, atol=1e-9), (med, med_o)
+        assert rem_o[5] and not rem_o[:5].any()
+    # inside mh_process (params.compatibility_check = 1) on the bundled pair, against the oracle pipeline with the same step
+    from ref_pipeline import oracle_process
+
+    g = np.load(os.path.join(GOLD, "barrsmith_hotpath_input.npz"))
+    lab, Hh, K = mh.Context(mh.capi.default_params(compatibility_check=1)).process(g["pts"], g["aff"], g["F"])
+    lab_o, H_o, _ = oracle_process(g["pts"], g["aff"], g["F"], compatibility_check=True)
+    print(f"\n[parity] barrsmith with compatibility check: K gpu={K} oracle={len(H_o)} agreement={(lab == lab_o).mean():.4f}")
+    assert K == len(H_o) and (lab == lab_o).mean() == 1.0
+
+
 def _ari(a, b):
     """adjusted Rand index of two labelings (label ids may be permuted between runs)"""
     a = np.unique(a, return_inverse=True)[1]; b = np.unique(b, return_inverse=True)[1]

@@ -149,3 +149,64 @@ def test_cpp_shim_compiles_links_and_fails_loudly_without_a_gpu(mh, tmp_path):
         assert r.returncode == 0 and "ctx 0 0" in r.stdout
     else:
         assert r.returncode == 3 and "no CPU fallback" in r.stdout
+
+
+def _garbage_scene(mh, n=3000, planes=5, seed=3, garbage=60):
+    """ground-truth plane labels + one cluster made of outliers (it must be removed) + one tiny cluster (below min_inliers)"""
+    sc = mh.scenes.make_scene(n, planes, seed=seed)
+    lab = sc.gt.astype(np.int32).copy()
+    out_idx = np.where(lab < 0)[0]
+    lab[out_idx[:garbage]] = planes
+    lab[out_idx[garbage:garbage + 7]] = planes + 1
+    H = np.concatenate([sc.planes, sc.planes[:2]])
+    return sc, lab, H
+
+
+def test_compatibility_check_host_halves_replay_the_oracle(mh, orc):
+    """mh_compat_plan + mh_compat_decide (the host halves of mh_compatibility_check) driven with ORACLE-computed order
+    statistics in place of the GPU kernel's reproduce orc_compatibility_check: same rand() consumption, same medians — i.e.
+    the sampling replay (evolving point vector) and the stale-entry / off-by-one median replay are the reference's."""
+    C = ctypes
+    lib = mh.capi.lib()
+    sc, lab, H = _garbage_scene(mh)
+    K, N, trials = len(H), len(lab), 501
+    for min_inl, seed in ((20, 1), (4, 77)):
+        l_o, H_o, med_o, rem_o, rng_o = orc.compatibility_check(sc.pts, lab, H, sc.F, thr=2.2, min_inliers=min_inl, rng_state=seed)
+        tested = np.zeros(K, np.int32); members = np.zeros(N, np.int32); moff = np.zeros(K + 1, np.int32)
+        samples = np.zeros(K * trials * 3, np.int32); removed = np.zeros(K, np.int32)
+        T = C.c_int32(0); rng = C.c_uint32(seed)
+        ip = lambda a: a.ctypes.data_as(C.POINTER(C.c_int32))
+        dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+        assert lib.mh_compat_plan(ip(lab), N, K, min_inl, C.byref(rng), ip(tested), C.byref(T), ip(members), ip(moff), ip(samples),
+                                  ip(removed)) == 0
+        assert rng.value == rng_o                                  # same number of rand() draws
+        T = T.value
+        stats = np.zeros((T, trials, 8))
+        for k in range(T):
+            mem = members[moff[k]:moff[k + 1]]
+            assert np.array_equal(mem, np.where(lab == tested[k])[0])
+            n = len(mem) - 3
+            m, lo = n // 2, max(0, n // 2 - 3)
+            for t in range(trials):
+                s3 = samples[(k * trials + t) * 3:(k * trials + t) * 3 + 3]
+                h = orc.homography_3pt(sc.pts[s3, :2], sc.pts[s3, 2:], sc.F).ravel()
+                q = sc.pts[np.setdiff1d(mem, s3)]
+                s = h[6] * q[:, 0] + h[7] * q[:, 1] + h[8]
+                x1 = (h[0] * q[:, 0] + h[1] * q[:, 1] + h[2]) / s; y1 = (h[3] * q[:, 0] + h[4] * q[:, 1] + h[5]) / s
+                d = np.sort((q[:, 2] - x1) ** 2 + (q[:, 3] - y1) ** 2)
+                w = np.full(8, np.inf); w[5:] = -np.inf
+                hi = min(n - 1, m + 1)
+                w[:hi - lo + 1] = d[lo:hi + 1]
+                top = d[::-1][:3]; w[5:5 + len(top)] = top
+                stats[k, t] = w
+        lab2, H2 = lab.copy(), np.ascontiguousarray(H.reshape(-1, 9)).copy()
+        Kio = C.c_int32(K); med = np.zeros(K)
+        assert lib.mh_compat_decide(ip(tested), T, ip(moff), dp(stats), C.c_double(2.2), ip(removed), N, ip(lab2), dp(H2),
+                                    C.byref(Kio), dp(med)) == 0
+        assert np.array_equal(removed.astype(bool), rem_o) and Kio.value == len(H_o)
+        assert np.array_equal(lab2, l_o) and np.array_equal(H2[:Kio.value], H_o)
+        ok = ~np.isnan(med_o)
+        assert np.array_equal(np.isnan(med), np.isnan(med_o)) and np.allclose(med[ok], med_o[ok], rtol=1e-9, atol=0)
+        assert rem_o[len(sc.planes)] and not rem_o[:len(sc.planes)].any()   # the garbage cluster goes, the planes stay
+        # the 7-member outlier cluster: removed untested when below min_inliers, tested (n >= 4, even-length median) and removed otherwise
+        assert rem_o[len(sc.planes) + 1] and np.isnan(med_o[len(sc.planes) + 1]) == (min_inl > 7)
