@@ -183,11 +183,12 @@ static int64_t total_energy(const int32_t* cost, int N, int L, int potts, const 
 // can tell whether the result still holds.
 // ---------------------------------------------------------------------------
 struct MoveWS {   // per-thread scratch
-  std::vector<int> var, cand, work;
+  std::vector<int> var, cand, work, fsw;
+  std::vector<char> sw_mark, state;
   std::vector<int32_t> trial;
-  std::vector<int64_t> src, snk, Wcur, Dcur;
+  std::vector<int64_t> src, snk, Wcur, Ucur, Dcur;
   MaxFlow mf;
-  void prepare(int N) { if ((int)var.size() != N) { var.assign(N, -1); trial.assign(N, 0); } }
+  void prepare(int N) { if ((int)var.size() != N) { var.assign(N, -1); trial.assign(N, 0); sw_mark.assign(N, 0); } }
 };
 struct MoveResult {
   int alpha = -1;
@@ -206,18 +207,26 @@ static void eval_move(const MoveProblem& P, const int32_t* lab, int alpha, MoveW
   const int N = P.N, L = P.L, potts = P.potts;
   const int32_t* cost = P.cost;
   const SymGraph& g = *P.g;
-  std::vector<int>&var = ws.var, &cand = ws.cand, &work = ws.work;
-  std::vector<int64_t>&src = ws.src, &snk = ws.snk, &Wcur = ws.Wcur, &Dcur = ws.Dcur;
+  std::vector<int>&var = ws.var, &cand = ws.cand, &work = ws.work, &fsw = ws.fsw;
+  std::vector<char>& swm = ws.sw_mark;
+  std::vector<int64_t>&src = ws.src, &snk = ws.snk, &Wcur = ws.Wcur, &Ucur = ws.Ucur, &Dcur = ws.Dcur;
   r.alpha = alpha; r.delta = 0; r.sw.clear(); r.any_c0 = false;
   if (want_touched) r.touched.assign(((size_t)N + 63) / 64, 0);
-  // Exact reduction of the move's binary problem.  Let S be the set of sites that may still switch to alpha.  Switching
-  // site i (data cost rises by D_i) lowers its pairwise terms by at most
-  //     W_i(S) = SUM_{j : l_j = alpha or j in S} w_ij  -  SUM_{j fixed, l_j = l_i} w_ij
-  // (a fixed neighbour with another label costs w either way).  If D_i > W_i(S), dropping i from any switch set inside S
-  // strictly lowers the energy, so no minimiser inside S switches i: i is fixed and S shrinks.  Starting from all sites
-  // and iterating to the fixed point leaves the few sites near hypothesis alpha's support — often none, and then the move
-  // is a no-op that needs no flow.  Every minimiser lies inside the final S, so the reduced problem has the same
-  // minimisers and the same maximal one (the labelling GCO returns).
+  // Exact two-sided reduction of the move's binary problem.  Let S be the set of sites that may still switch to alpha and
+  // D_i the rise of site i's data cost when it does.
+  //  (keep)   Switching i lowers its pairwise terms by at most
+  //               W_i = SUM_{j : alpha already, or j in S} w_ij  -  SUM_{j keeps for sure, l_j = l_i} w_ij
+  //           (a sure keeper with another label costs w either way).  If D_i > W_i, dropping i from any switch set inside S
+  //           strictly lowers the energy: no minimiser switches i; i leaves S.
+  //  (switch) Switching i raises its pairwise terms by at most
+  //               U_i = SUM_{j not alpha, l_j = l_i} w_ij  -  SUM_{j : alpha already} w_ij
+  //           If D_i + U_i < 0, adding i to any switch set strictly lowers the energy: every minimiser switches i; i counts
+  //           as "alpha already" for its neighbours from then on.
+  // Both rules only ever tighten the other sites' bounds, so the work list below reaches the unique fixed point.  What is
+  // left for the flow network are the genuinely ambiguous sites — often none: cold sweeps are mostly sure switchers (the
+  // support of hypothesis alpha leaving the outlier label), later sweeps mostly sure keepers.  Every minimiser contains the
+  // sure switchers and lies inside S, so the reduced problem has the same minimisers and the same maximal one (the labelling
+  // GCO returns).
   cand.clear();
   for (int i = 0; i < N; ++i)
     if (lab[i] != alpha && (int64_t)cost[(size_t)i * L + alpha] - cost[(size_t)i * L + lab[i]] <= P.Wall[i]) {
@@ -226,109 +235,131 @@ static void eval_move(const MoveProblem& P, const int32_t* lab, int alpha, MoveW
     }
   if (cand.empty()) return;
   r.any_c0 = true;
-  // one pass for W_i(S), then a work list — dropping i lowers W_j of its surviving neighbours by w_ij (i can no longer turn
-  // alpha) and by another w_ij if l_j = l_i (i now certainly disagrees with alpha-j), which may drop them in turn
-  Wcur.resize(cand.size());
-  Dcur.resize(cand.size());
+  const size_t n0 = cand.size();
+  Wcur.resize(n0); Ucur.resize(n0); Dcur.resize(n0);
+  std::vector<char>& st = ws.state;   // per initial candidate: 0 = undecided, 1 = queued/decided keep, 2 = queued/decided switch
+  st.assign(n0, 0);
   work.clear();
-  for (size_t a = 0; a < cand.size(); ++a) {
+  for (size_t a = 0; a < n0; ++a) {
     const int i = cand[a];
-    int64_t Wi = 0;
     if (want_touched) {
       r.touched[(size_t)i >> 6] |= 1ull << (i & 63);
       for (int64_t k = g.off[i]; k < g.off[i + 1]; ++k) r.touched[(size_t)g.nbr[k] >> 6] |= 1ull << (g.nbr[k] & 63);
     }
     const int li = lab[i];
-    int32_t wsum = 0;   // branch-free: the tests are data-dependent coin flips
+    int32_t wsum = 0, usum = 0;   // branch-free: the tests are data-dependent coin flips
     for (int64_t k = g.off[i]; k < g.off[i + 1]; ++k) {
       const int j = g.nbr[k];
       const int lj = lab[j];
-      const int may = (lj == alpha) | (var[j] >= 0);
-      wsum += g.w[k] * (may - ((may ^ 1) & (lj == li)));
+      const int isA = lj == alpha, may = isA | (var[j] >= 0), same = lj == li;
+      wsum += g.w[k] * (may - ((may ^ 1) & same));
+      usum += g.w[k] * (((isA ^ 1) & same) - isA);
     }
-    Wi = (int64_t)potts * wsum;
-    Wcur[a] = Wi;
-    Dcur[a] = (int64_t)cost[(size_t)i * L + alpha] - cost[(size_t)i * L + lab[i]];
+    Wcur[a] = (int64_t)potts * wsum;
+    Ucur[a] = (int64_t)potts * usum;
+    Dcur[a] = (int64_t)cost[(size_t)i * L + alpha] - cost[(size_t)i * L + li];
   }
-  for (size_t a = 0; a < cand.size(); ++a)
-    if (Dcur[a] > Wcur[a]) { work.push_back((int)a); Dcur[a] = INT64_MIN; }   // INT64_MIN marks "queued / dropped"
+  for (size_t a = 0; a < n0; ++a) {
+    if (Dcur[a] > Wcur[a]) { st[a] = 1; work.push_back((int)a); }
+    else if (Dcur[a] + Ucur[a] < 0) { st[a] = 2; work.push_back((int)a); }
+  }
+  fsw.clear();
   for (size_t q = 0; q < work.size(); ++q) {
-    const int i = cand[work[q]];
-    var[i] = -1;
+    const int a = work[q], i = cand[a];
+    const bool keeps = st[a] == 1;
+    if (!keeps) { swm[i] = 1; fsw.push_back(i); }
     for (int64_t k = g.off[i]; k < g.off[i + 1]; ++k) {
       const int j = g.nbr[k];
       const int b2 = var[j];
-      if (b2 < 0 || Dcur[b2] == INT64_MIN) continue;
-      Wcur[b2] -= (int64_t)potts * g.w[k] * (lab[j] == lab[i] ? 2 : 1);
-      if (Dcur[b2] > Wcur[b2]) { work.push_back(b2); Dcur[b2] = INT64_MIN; }
+      if (b2 < 0 || st[b2] != 0) continue;
+      const int64_t d = (int64_t)potts * g.w[k] * (lab[j] == lab[i] ? 2 : 1);
+      if (keeps) {   // i can no longer turn alpha (-w), and now certainly disagrees with an alpha-j if l_j = l_i (-w)
+        Wcur[b2] -= d;
+        if (Dcur[b2] > Wcur[b2]) { st[b2] = 1; work.push_back(b2); }
+      } else {       // i is alpha from now on: its pair term can only fall when j switches (-w), and no longer rises (-w if l_j = l_i)
+        Ucur[b2] -= d;
+        if (Dcur[b2] + Ucur[b2] < 0) { st[b2] = 2; work.push_back(b2); }
+      }
     }
   }
-  if (!work.empty()) {
+  // survivors = the flow network's nodes; decided sites leave `var`
+  {
     size_t keep = 0;
-    for (size_t a = 0; a < cand.size(); ++a)
-      if (Dcur[a] != INT64_MIN) cand[keep++] = cand[a];
+    for (size_t a = 0; a < n0; ++a) {
+      if (st[a] == 0) cand[keep++] = cand[a];
+      else var[cand[a]] = -1;
+    }
     cand.resize(keep);
   }
-  if (cand.empty()) return;
+  if (cand.empty() && fsw.empty()) return;
   for (size_t a = 0; a < cand.size(); ++a) var[cand[a]] = (int)a;
-  size_t arcs = 0;
-  for (int i : cand) arcs += (size_t)(g.off[i + 1] - g.off[i]);
-  MaxFlow& mf = ws.mf;
-  mf.reset((int)cand.size(), 2 * arcs + 2 * cand.size());
-  src.assign(cand.size(), 0);
-  snk.assign(cand.size(), 0);
-  int64_t before = 0;   // energy of the terms below under the current labelling = SUM of the source-arc payments
-  for (size_t a = 0; a < cand.size(); ++a) {
-    const int i = cand[a], li = lab[i];
-    // x = 0 (source side) takes alpha and pays E0 on the arc to the sink; x = 1 keeps its label.  Per neighbour j:
-    //   l_j = alpha            : pay w iff i keeps its label                                  -> source arc += w
-    //   j fixed (l_j != alpha) : alpha pays w, keeping pays w [l_i != l_j]                     -> sink += w, source += w [..]
-    //   j in the network, j < i: E00 = 0, E01 = E10 = w, E11 = w [l_i != l_j]: pay E11 on i's source arc, remaining
-    //                            table [0, w; w - E11, 0] becomes the arc pair
-    // (sums kept branch-free; only the arc insertion branches)
-    int32_t s_w = 0, t_w = 0;
-    for (int64_t k = g.off[i]; k < g.off[i + 1]; ++k) {
-      const int j = g.nbr[k], lj = lab[j], vj = var[j], w = g.w[k];
-      const int isA = lj == alpha, inS = vj >= 0, diff = li != lj;
-      const int fixed = (isA | inS) ^ 1, both = inS & (j < i);
-      s_w += w * (isA | (diff & (fixed | both)));
-      t_w += w * fixed;
-      if (both) mf.add_edge((int)a, vj, (int64_t)potts * w, (int64_t)potts * w * (diff ^ 1));
-    }
-    snk[a] = cost[(size_t)i * L + alpha] + (int64_t)potts * t_w;
-    src[a] = cost[(size_t)i * L + li] + (int64_t)potts * s_w;
-    before += src[a];
-  }
-  for (size_t a = 0; a < cand.size(); ++a) mf.add_terminal((int)a, src[a], snk[a]);
-  mf.solve();
-  bool any = false;
   std::vector<int32_t>& trial = ws.trial;
-  for (size_t a = 0; a < cand.size(); ++a) {
-    const bool sw = !mf.sink_side((int)a);
-    trial[cand[a]] = sw ? alpha : lab[cand[a]];
-    any |= sw;
+  bool any = !fsw.empty();
+  if (!cand.empty()) {
+    size_t arcs = 0;
+    for (int i : cand) arcs += (size_t)(g.off[i + 1] - g.off[i]);
+    MaxFlow& mf = ws.mf;
+    mf.reset((int)cand.size(), 2 * arcs + 2 * cand.size());
+    src.assign(cand.size(), 0);
+    snk.assign(cand.size(), 0);
+    for (size_t a = 0; a < cand.size(); ++a) {
+      const int i = cand[a], li = lab[i];
+      // x = 0 (source side) takes alpha and pays E0 on the arc to the sink; x = 1 keeps its label.  Per neighbour j:
+      //   alpha already (or a sure switcher): pay w iff i keeps its label                      -> source arc += w
+      //   j keeps for sure (l_j != alpha)    : alpha pays w, keeping pays w [l_i != l_j]        -> sink += w, source += w [..]
+      //   j in the network, j < i            : E00 = 0, E01 = E10 = w, E11 = w [l_i != l_j]: pay E11 on i's source arc, the
+      //                                        remaining table [0, w; w - E11, 0] becomes the arc pair
+      // (sums kept branch-free; only the arc insertion branches)
+      int32_t s_w = 0, t_w = 0;
+      for (int64_t k = g.off[i]; k < g.off[i + 1]; ++k) {
+        const int j = g.nbr[k], lj = lab[j], vj = var[j], w = g.w[k];
+        const int isA = (lj == alpha) | swm[j], inS = vj >= 0, diff = li != lj;
+        const int fixed = (isA | inS) ^ 1, both = inS & (j < i);
+        s_w += w * (isA | (diff & (fixed | both)));
+        t_w += w * fixed;
+        if (both) mf.add_edge((int)a, vj, (int64_t)potts * w, (int64_t)potts * w * (diff ^ 1));
+      }
+      snk[a] = cost[(size_t)i * L + alpha] + (int64_t)potts * t_w;
+      src[a] = cost[(size_t)i * L + li] + (int64_t)potts * s_w;
+    }
+    for (size_t a = 0; a < cand.size(); ++a) mf.add_terminal((int)a, src[a], snk[a]);
+    mf.solve();
+    for (size_t a = 0; a < cand.size(); ++a) {
+      const bool sw = !mf.sink_side((int)a);
+      trial[cand[a]] = sw ? alpha : lab[cand[a]];
+      any |= sw;
+    }
   }
   if (any) {
-    // energy of the same terms under the trial labelling (trial = lab outside the network)
-    int64_t after = 0;
-    for (size_t a = 0; a < cand.size(); ++a) {
-      const int i = cand[a], ti = trial[i];
+    // energy of every term that involves a network site or a sure switcher, before and after (each pair once)
+    int64_t before = 0, after = 0;
+    auto tally = [&](int i, int ti) {
+      const int li = lab[i];
+      before += cost[(size_t)i * L + li];
       after += cost[(size_t)i * L + ti];
-      int32_t cut = 0;
+      int32_t cb = 0, ca = 0;
       for (int64_t k = g.off[i]; k < g.off[i + 1]; ++k) {
-        const int j = g.nbr[k], vj = var[j];
-        const int lj = vj >= 0 ? trial[j] : lab[j];
-        cut += g.w[k] * (((vj < 0) | (j < i)) & (ti != lj));
+        const int j = g.nbr[k], vj = var[j], lj = lab[j];
+        const int inU = (vj >= 0) | swm[j];
+        const int tj = swm[j] ? alpha : (vj >= 0 ? trial[j] : lj);
+        const int once = (inU ^ 1) | (j < i);
+        cb += g.w[k] * (once & (li != lj));
+        ca += g.w[k] * (once & (ti != tj));
       }
-      after += (int64_t)potts * cut;
-    }
+      before += (int64_t)potts * cb;
+      after += (int64_t)potts * ca;
+    };
+    for (int i : cand) tally(i, trial[i]);
+    for (int i : fsw) tally(i, alpha);
     if (after < before) {   // GCO accepts a move only if it strictly lowers the energy
       r.delta = after - before;
+      for (int i : fsw) r.sw.push_back(i);
       for (int i : cand)
         if (trial[i] == alpha) r.sw.push_back(i);
     }
   }
   for (int i : cand) var[i] = -1;
+  for (int i : fsw) swm[i] = 0;
 }
 
 // ---------------------------------------------------------------------------
