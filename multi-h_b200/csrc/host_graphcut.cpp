@@ -194,11 +194,13 @@ struct MoveResult {
   int alpha = -1;
   int64_t delta = 0;               // energy change if applied (< 0, or 0 with an empty switch list)
   std::vector<int> sw;             // sites that switch to alpha
-  std::vector<uint64_t> touched;   // bitset over sites: C0 and its neighbours (filled only on request)
+  std::vector<uint64_t> touched;   // bitset over sites: the initial candidates C0 (what the move read = C0 and its neighbours)
   bool any_c0 = false;
 };
 struct MoveProblem {
   const int32_t* cost; int N, L, potts;
+  const int32_t* costT;            // label-major copy [L][N]: a move's scan reads one contiguous row
+  const int32_t* cur;              // cost of every site at its current label (kept up to date by the sweep)
   const SymGraph* g;
   const int64_t* Wall;             // SUM_j w_ij
 };
@@ -228,11 +230,14 @@ static void eval_move(const MoveProblem& P, const int32_t* lab, int alpha, MoveW
   // sure switchers and lies inside S, so the reduced problem has the same minimisers and the same maximal one (the labelling
   // GCO returns).
   cand.clear();
-  for (int i = 0; i < N; ++i)
-    if (lab[i] != alpha && (int64_t)cost[(size_t)i * L + alpha] - cost[(size_t)i * L + lab[i]] <= P.Wall[i]) {
-      var[i] = (int)cand.size();
-      cand.push_back(i);
-    }
+  {
+    const int32_t* ca = P.costT + (size_t)alpha * N;
+    const int32_t* cc = P.cur;
+    const int64_t* wa = P.Wall;
+    for (int i = 0; i < N; ++i)
+      if (((int64_t)ca[i] - cc[i] <= wa[i]) & (lab[i] != alpha)) cand.push_back(i);
+    for (size_t a = 0; a < cand.size(); ++a) var[cand[a]] = (int)a;
+  }
   if (cand.empty()) return;
   r.any_c0 = true;
   const size_t n0 = cand.size();
@@ -242,10 +247,7 @@ static void eval_move(const MoveProblem& P, const int32_t* lab, int alpha, MoveW
   work.clear();
   for (size_t a = 0; a < n0; ++a) {
     const int i = cand[a];
-    if (want_touched) {
-      r.touched[(size_t)i >> 6] |= 1ull << (i & 63);
-      for (int64_t k = g.off[i]; k < g.off[i + 1]; ++k) r.touched[(size_t)g.nbr[k] >> 6] |= 1ull << (g.nbr[k] & 63);
-    }
+    if (want_touched) r.touched[(size_t)i >> 6] |= 1ull << (i & 63);
     const int li = lab[i];
     int32_t wsum = 0, usum = 0;   // branch-free: the tests are data-dependent coin flips
     for (int64_t k = g.off[i]; k < g.off[i + 1]; ++k) {
@@ -529,7 +531,15 @@ mh_status alpha_expansion(const int32_t* cost, int N, int L, int potts, const in
 
   std::vector<int64_t> Wall(N);
   for (int i = 0; i < N; ++i) Wall[i] = (int64_t)potts * prepared.Wall[i];
-  const MoveProblem P{cost, N, L, potts, &g, Wall.data()};
+  // label-major copy of the costs and the cost of every site at its current label: a move's candidate scan becomes a
+  // contiguous pass (the site-major matrix would be read with stride L)
+  std::vector<int32_t> costT((size_t)N * L), cur(N);
+  for (int i = 0; i < N; ++i) {
+    const int32_t* row = cost + (size_t)i * L;
+    for (int l = 0; l < L; ++l) costT[(size_t)l * N + i] = row[l];
+    cur[i] = row[lab[i]];
+  }
+  const MoveProblem P{cost, N, L, potts, costT.data(), cur.data(), &g, Wall.data()};
 
   MovePool* pool = (L >= 4 && (int64_t)N * L >= 4096) ? MovePool::acquire() : nullptr;
   const int nthreads = pool ? pool->threads() : 1;
@@ -553,14 +563,18 @@ mh_status alpha_expansion(const int32_t* cost, int N, int L, int potts, const in
   auto clean_since = [&](int alpha, const std::vector<uint64_t>& touched, bool any_c0, size_t from) {
     for (size_t k = from; k < log.size(); ++k) {
       const int d = log[k];
-      if (any_c0 && ((touched[(size_t)d >> 6] >> (d & 63)) & 1ull)) return false;
+      if (any_c0) {   // d in C0, or a neighbour of a C0 site (the graph is symmetric)
+        if ((touched[(size_t)d >> 6] >> (d & 63)) & 1ull) return false;
+        for (int64_t q = g.off[d]; q < g.off[d + 1]; ++q)
+          if ((touched[(size_t)g.nbr[q] >> 6] >> (g.nbr[q] & 63)) & 1ull) return false;
+      }
       if (lab[d] != alpha && (int64_t)cost[(size_t)d * L + alpha] - cost[(size_t)d * L + lab[d]] <= Wall[d]) return false;
     }
     return true;
   };
   auto known_idle = [&](int alpha) {
     Memo& m = memo[alpha];
-    if (!m.valid || log.size() - m.pos > (size_t)N) return false;   // (a long log: evaluating is cheaper than checking)
+    if (!m.valid || log.size() - m.pos > 256) return false;   // (many changes: evaluating is cheaper than checking, and rarely idle)
     if (!clean_since(alpha, m.touched, m.any_c0, m.pos)) return false;
     m.pos = log.size();
     return true;
@@ -594,7 +608,7 @@ mh_status alpha_expansion(const int32_t* cost, int N, int L, int potts, const in
         const bool usable = pool && nw > 1 && speculated[j] && clean_since(alpha, res[j].touched, res[j].any_c0, snapshot);
         if (!usable) eval_move(P, lab, alpha, ws[0], res[j], true);
         if (!res[j].sw.empty()) {
-          for (int i : res[j].sw) { lab[i] = alpha; log.push_back(i); }
+          for (int i : res[j].sw) { lab[i] = alpha; cur[i] = cost[(size_t)i * L + alpha]; log.push_back(i); }
           E_delta += res[j].delta;
           idle_moves = 0;
         }
