@@ -151,14 +151,18 @@ def test_cpp_shim_compiles_links_and_fails_loudly_without_a_gpu(mh, tmp_path):
         assert r.returncode == 3 and "no CPU fallback" in r.stdout
 
 
-def _garbage_scene(mh, n=3000, planes=5, seed=3, garbage=60):
+def _garbage_scene(mh, n=3000, planes=5, seed=3, garbage=60, tiny=()):
     """ground-truth plane labels + one cluster made of outliers (it must be removed) + one tiny cluster (below min_inliers)"""
     sc = mh.scenes.make_scene(n, planes, seed=seed)
     lab = sc.gt.astype(np.int32).copy()
     out_idx = np.where(lab < 0)[0]
     lab[out_idx[:garbage]] = planes
     lab[out_idx[garbage:garbage + 7]] = planes + 1
-    H = np.concatenate([sc.planes, sc.planes[:2]])
+    extra, pos = 2, garbage + 7
+    for size in tiny:                      # tiny clusters: every small-n case of the median replay (n = members - 3 = 1, 2, 3, ...)
+        lab[out_idx[pos:pos + size]] = planes + extra
+        extra += 1; pos += size
+    H = np.concatenate([sc.planes, np.repeat(sc.planes[:1], extra, axis=0)])
     return sc, lab, H
 
 
@@ -168,9 +172,9 @@ def test_compatibility_check_host_halves_replay_the_oracle(mh, orc):
     the sampling replay (evolving point vector) and the stale-entry / off-by-one median replay are the reference's."""
     C = ctypes
     lib = mh.capi.lib()
-    sc, lab, H = _garbage_scene(mh)
+    sc, lab, H = _garbage_scene(mh, tiny=(4, 5, 6, 8, 9))
     K, N, trials = len(H), len(lab), 501
-    for min_inl, seed in ((20, 1), (4, 77)):
+    for min_inl, seed in ((20, 1), (4, 77), (0, 5)):
         l_o, H_o, med_o, rem_o, rng_o = orc.compatibility_check(sc.pts, lab, H, sc.F, thr=2.2, min_inliers=min_inl, rng_state=seed)
         tested = np.zeros(K, np.int32); members = np.zeros(N, np.int32); moff = np.zeros(K + 1, np.int32)
         samples = np.zeros(K * trials * 3, np.int32); removed = np.zeros(K, np.int32)
