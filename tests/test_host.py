@@ -64,14 +64,15 @@ def test_alpha_expansion_equals_reference_gco(mh, orc, radius):
     assert e2 == e_ref2 and np.array_equal(l2, l_ref2)
 
 
-@pytest.mark.parametrize("threads", ["1", "8"])
-def test_alpha_expansion_random_problems_equal_reference_gco(mh, orc, threads, monkeypatch):
+@pytest.mark.parametrize("threads,solver", [("1", "auto"), ("8", "auto"), ("1", "pr"), ("8", "dinic")])
+def test_alpha_expansion_random_problems_equal_reference_gco(mh, orc, threads, solver, monkeypatch):
     """Randomised check of everything the host expansion does beyond a plain max-flow per move — exact candidate reduction,
-    move memo, speculative parallel evaluation (MH_GC_THREADS) — against the reference GCO: random graphs (multi-edges,
+    move memo, speculative parallel evaluation (MH_GC_THREADS), two max-flow solvers (MH_GC_SOLVER) — against the reference GCO: random graphs (multi-edges,
     isolated sites), coarse costs with many ties, zero / huge Potts weights, cold and warm starts, capped cycles."""
     if orc.ref_lib() is None:
         pytest.skip("oracle/_ref not built")
     monkeypatch.setenv("MH_GC_THREADS", threads)
+    monkeypatch.setenv("MH_GC_SOLVER", solver)   # both max-flow solvers (Dinic / push-relabel) must give the reference's cut
     rng = np.random.default_rng(1234)
     for trial in range(60):
         N = int(rng.integers(2, 400))
