@@ -43,6 +43,13 @@ def test_neighbourhood_matches_oracle(mh, orc):
         o2, a2 = mh.capi.neighbourhood(sc.pts, radius, k)
         assert np.array_equal(o1, o2) and np.array_equal(a1, a2), (radius, k)
     assert np.diff(o2).max() == 31  # FLANN checks=32 cap
+    # exact duplicates (d2 = 0 ties are resolved by index), a handful of points, a single point
+    dup = np.concatenate([sc.pts[:300], sc.pts[:120], sc.pts[:7]])
+    for pts in (dup, sc.pts[:3], sc.pts[:1]):
+        for radius, k in ((0.0, 31), (50.0, 4), (1e4, 31), (1e4, 0)):
+            o1, a1 = orc.radius_neighbours(pts, radius, k)
+            o2, a2 = mh.capi.neighbourhood(pts, radius, k)
+            assert np.array_equal(o1, o2) and np.array_equal(a1, a2), (len(pts), radius, k)
 
 
 @pytest.mark.parametrize("radius", [0.0, 15.0, 40.0])
