@@ -301,7 +301,72 @@ def prefilter_vectors():
     np.savez_compressed(os.path.join(HERE, "golden_prefilter.npz"), **out)
 
 
+def compatibility_check(pts, labels, K, F, thr=2.2, min_inliers=20, seed=1):  # MultiH.cpp:100-222, serial draw order
+    """Transliteration with Python lists standing in for the std::vectors (erase / resize / write-back at the end) and the MSVC
+    rand() the reference is built against; the 3-point fits go through the cv2-based get_homography_3pt above."""
+    hold = [seed]
+
+    def rand():
+        hold[0] = (hold[0] * 214013 + 2531011) & 0xFFFFFFFF
+        return (hold[0] >> 16) & 0x7FFF
+
+    medians, removed = np.full(K, np.nan), np.zeros(K, dtype=bool)
+    for c in range(K):
+        v = [tuple(p) for p in pts[labels == c]]                          # :106-114
+        N = len(v)
+        trials = max(501, min(501, N * (N - 1) * (N - 2) // 6))           # :130
+        if N >= max(min_inliers, 4):                                      # :138
+            dist = [0.0] * N                                              # :140 (size N, only N - 3 entries rewritten per trial)
+            distances = []
+            for _ in range(trials):
+                mss = []
+                for _j in range(3):
+                    idx = int((len(v) - 1) * (rand() / 32767.0))          # :145
+                    mss.append(v.pop(idx))                                # :147-153
+                m = np.array(mss)
+                h = get_homography_3pt(m[:, :2], m[:, 2:], F)             # :157 (no refinement)
+                for j, (ox1, oy1, ox2, oy2) in enumerate(v):              # :162-175
+                    sden = h[6] * ox1 + h[7] * oy1 + h[8]
+                    x1 = (h[0] * ox1 + h[1] * oy1 + h[2]) / sden
+                    y1 = (h[3] * ox1 + h[4] * oy1 + h[5]) / sden
+                    dist[j] = (ox2 - x1) ** 2 + (oy2 - y1) ** 2
+                dist.sort()                                               # :177 — all N entries
+                n = len(v)
+                distances.append(dist[n // 2] if n % 2 else 0.5 * (dist[n // 2] + dist[n // 2 + 1]))   # :178
+                v = v + [None] * 3                                        # :180-181 resize(N)
+                for j in range(3):
+                    v[N - j - 1] = mss[j]                                 # :183-194
+            distances.sort()
+            medians[c] = distances[trials // 2] if trials % 2 else 0.5 * (distances[trials // 2] + distances[trials // 2 + 1])
+            removed[c] = medians[c] > thr * thr * 81.0 / 16.0             # :202
+        elif N < min_inliers:
+            removed[c] = True                                             # :207-208
+    return medians, removed, hold[0]
+
+
+def compatibility_vectors():
+    """golden_compat.npz: a small labelled scene (three planes, one cluster of outliers, one 6-member cluster)."""
+    sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+    import multih_b200 as m
+
+    sc = m.scenes.make_scene(420, 3, seed=17)
+    lab = sc.gt.astype(np.int32).copy()
+    out_idx = np.where(lab < 0)[0]
+    lab[out_idx[:25]] = 3
+    lab[out_idx[25:31]] = 4
+    out = dict(pts=sc.pts, labels=lab, F=sc.F)
+    for tag, min_inl, seed in (("a", 20, 1), ("b", 4, 4242)):
+        med, rem, rng = compatibility_check(sc.pts, lab, 5, sc.F, 2.2, min_inl, seed)
+        out.update({f"{tag}_min_inliers": min_inl, f"{tag}_seed": seed, f"{tag}_medians": med, f"{tag}_removed": rem, f"{tag}_rng": rng})
+        print("compat", tag, med, rem)
+    np.savez_compressed(os.path.join(HERE, "golden_compat.npz"), **out)
+
+
 if __name__ == "__main__":
-    small_vectors()
-    barrsmith_fixture()
-    prefilter_vectors()
+    if len(sys.argv) > 1 and sys.argv[1] == "compat":
+        compatibility_vectors()
+    else:
+        small_vectors()
+        barrsmith_fixture()
+        prefilter_vectors()
+        compatibility_vectors()

@@ -163,3 +163,21 @@ def test_meanshift_terminates_on_a_cycling_trajectory(orc):
     fo = orc.features10(orc.haf_hypotheses(sc.pts, sc.aff, sc.F), sc.pts, 0.005)
     cen, asg, _, st = orc.meanshift(fo, 2.2)
     assert st[0] > 0 and st[1] >= 200 and len(cen) > 10 and (asg >= 0).all()
+
+
+def test_compatibility_check_golden(orc):
+    """orc_compatibility_check against tests/golden/golden_compat.npz — an independent transliteration of
+    HomographyCompatibilityCheck (MultiH.cpp:100-222) with Python lists for the std::vectors and the cv2-based 3-point fit
+    (make_golden.py): same clusters removed, same rand() consumption, medians to 1e-6 (own SVD vs cv2.invert(DECOMP_SVD))."""
+    g = np.load(os.path.join(GOLD, "golden_compat.npz"))
+    for tag in ("a", "b"):
+        lab, H, med, rem, rng = orc.compatibility_check(g["pts"], g["labels"], np.tile(np.eye(3).ravel(), (5, 1)), g["F"], 2.2,
+                                                        int(g[f"{tag}_min_inliers"]), int(g[f"{tag}_seed"]))
+        assert np.array_equal(rem, g[f"{tag}_removed"]) and rng == int(g[f"{tag}_rng"])
+        gm = g[f"{tag}_medians"]
+        ok = ~np.isnan(gm)
+        assert np.array_equal(np.isnan(med), np.isnan(gm)) and np.allclose(med[ok], gm[ok], rtol=1e-6, atol=0), (med, gm)
+        keep = np.where(~rem)[0]
+        assert len(H) == len(keep) and set(np.unique(lab)) <= set(range(-1, len(keep)))
+        for new, old in enumerate(keep):   # survivors keep their members, in order; removed clusters' members become outliers
+            assert np.array_equal(lab == new, g["labels"] == old)
