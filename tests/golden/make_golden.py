@@ -344,6 +344,89 @@ def compatibility_check(pts, labels, K, F, thr=2.2, min_inliers=20, seed=1):  # 
     return medians, removed, hold[0]
 
 
+def meanshift_cluster(data, bw, seed=1, max_window_iters=200):  # MeanShiftClustering.h:22-157 (T = double)
+    """Transliteration in numpy with the MSVC rand(); `max_window_iters` is the one deliberate deviation shared by oracle and
+    kernel (the reference's while(1) at :62 does not return when the mean cycles)."""
+    hold = [seed]
+
+    def rand():
+        hold[0] = (hold[0] * 214013 + 2531011) & 0xFFFFFFFF
+        return (hold[0] >> 16) & 0x7FFF
+
+    num = len(data)
+    band_sq, stop = bw * bw, 1e-3 * bw                                   # :31, :48
+    init = list(range(num))
+    visited = np.zeros(num, dtype=bool)
+    cents, votes = [], []
+    traj = iters = 0
+    while init:                                                          # :52
+        rnd = rand() / 32767.0
+        st = init[int(math.floor(rnd * (len(init) - 1) + 0.5))]         # :54-56 (round)
+        mean = data[st].copy()
+        this_votes = np.zeros(num, dtype=np.int64)
+        traj += 1
+        w = 0
+        while True:                                                      # :62
+            iters += 1; w += 1
+            old = mean.copy()
+            sq = np.sqrt((old[None, :] - data) ** 2).sum(1)              # :76-83: SUM_j sqrt(d_j^2) = L1
+            inside = sq < band_sq                                        # :85
+            this_votes[inside] += 1
+            visited[inside] = True
+            acc = np.zeros(data.shape[1])
+            for i in np.where(inside)[0]:                                # :89 (same summation order as the reference loop)
+                acc = acc + data[i]
+            mean = acc / inside.sum()                                    # :96
+            if np.linalg.norm(mean - old) < stop or w >= max_window_iters:   # :98
+                merge = -1
+                for cn, c in enumerate(cents):                           # :101-109
+                    if np.linalg.norm(mean - c) < bw / 2:
+                        merge = cn
+                        break
+                if merge > -1:
+                    cents[merge] = 0.5 * (cents[merge] + mean)           # :113
+                    votes[merge] = votes[merge] + this_votes
+                else:
+                    cents.append(mean)
+                    votes.append(this_votes)
+                break
+        init = [i for i in range(num) if not visited[i]]                 # :124-130
+    best, idx = np.zeros(num, dtype=np.int64), np.full(num, -1)
+    for r, v in enumerate(votes):                                        # :136-146: most votes, first wins ties
+        upd = best < v
+        best[upd] = v[upd]
+        idx[upd] = r
+    return np.array(cents), idx, hold[0], (traj, iters)
+
+
+def meanshift_vectors():
+    """golden_meanshift.npz: the 10-D features of a small scene (EstablishStablePointSets) and a 6-D set (MergingStep)."""
+    sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+    import multih_b200 as m
+
+    sc = m.scenes.make_scene(260, 3, seed=23)
+    F = sc.F
+    e = epipole2(F)
+    H = np.array([get_homography_haf(sc.pts[i], sc.aff[i], F, e) for i in range(len(sc.pts))])
+    f10 = []
+    for h, p in zip(H, sc.pts):                                          # MultiH.cpp:612-646
+        x1, y1 = h[2] / h[8], h[5] / h[8]
+        x2, y2 = (h[0] + h[2]) / (h[6] + h[8]), (h[3] + h[5]) / (h[6] + h[8])
+        x3, y3 = (h[1] + h[2]) / (h[7] + h[8]), (h[4] + h[5]) / (h[7] + h[8])
+        f10.append([x1, x2, x3, y1, y2, y3] + list(0.005 * p))
+    f10 = np.array(f10)
+    f10 = f10[np.isfinite(f10).all(1)]
+    rng = np.random.default_rng(5)
+    f6 = np.concatenate([rng.normal(0, 0.4, (25, 6)) + k * 3.0 for k in range(4)])
+    out = {}
+    for tag, X, seed in (("f10", f10, 1), ("f6", f6, 777)):
+        c, idx, st, stats = meanshift_cluster(X, 2.2, seed)
+        out.update({f"{tag}_data": X, f"{tag}_seed": seed, f"{tag}_centres": c, f"{tag}_assign": idx, f"{tag}_rng": st,
+                    f"{tag}_stats": np.array(stats)})
+        print("meanshift", tag, X.shape, "->", len(c), "centres", stats)
+    np.savez_compressed(os.path.join(HERE, "golden_meanshift.npz"), **out)
+
+
 def compatibility_vectors():
     """golden_compat.npz: a small labelled scene (three planes, one cluster of outliers, one 6-member cluster)."""
     sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
@@ -365,8 +448,11 @@ def compatibility_vectors():
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "compat":
         compatibility_vectors()
+    elif len(sys.argv) > 1 and sys.argv[1] == "meanshift":
+        meanshift_vectors()
     else:
         small_vectors()
         barrsmith_fixture()
         prefilter_vectors()
         compatibility_vectors()
+        meanshift_vectors()

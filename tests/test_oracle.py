@@ -181,3 +181,15 @@ def test_compatibility_check_golden(orc):
         assert len(H) == len(keep) and set(np.unique(lab)) <= set(range(-1, len(keep)))
         for new, old in enumerate(keep):   # survivors keep their members, in order; removed clusters' members become outliers
             assert np.array_equal(lab == new, g["labels"] == old)
+
+
+def test_meanshift_golden(orc):
+    """orc_meanshift against tests/golden/golden_meanshift.npz — an independent numpy transliteration of
+    MeanShiftClustering<double>::Cluster (MeanShiftClustering.h:22-157) with the MSVC rand() (make_golden.py): same
+    trajectories, window iterations, rand() consumption and assignments; centres to 1e-9."""
+    g = np.load(os.path.join(GOLD, "golden_meanshift.npz"))
+    for tag in ("f10", "f6"):
+        cen, asg, rng, stats = orc.meanshift(g[f"{tag}_data"], 2.2, 0, int(g[f"{tag}_seed"]))
+        assert tuple(stats) == tuple(g[f"{tag}_stats"]) and rng == int(g[f"{tag}_rng"])
+        assert cen.shape == g[f"{tag}_centres"].shape and np.allclose(cen, g[f"{tag}_centres"], rtol=1e-9, atol=1e-9)
+        assert np.array_equal(asg, g[f"{tag}_assign"])
