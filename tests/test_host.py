@@ -52,6 +52,29 @@ def test_neighbourhood_matches_oracle(mh, orc):
             assert np.array_equal(o1, o2) and np.array_equal(a1, a2), (len(pts), radius, k)
 
 
+def test_neighbourhood_definition_against_flann_radius_match(mh):
+    """What the restated neighbourhood stands for.  The reference calls FlannBasedMatcher::radiusMatch with FLANN's defaults
+    (MultiH.cpp:252-253): randomised KD-trees with checks = 32, so a query returns at most 32 examined points (itself among
+    them) — NOT the 200-px ball, which holds ~300 points on barrsmith.  cv2's FlannBasedMatcher shows exactly that, and its
+    lists are mostly the nearest points: the exactly defined set used here ("31 nearest within the radius, ties by index") is
+    what FLANN approximates (overlap ~3/4; FLANN's own lists are not reproducible run to run)."""
+    cv2 = pytest.importorskip("cv2")
+    g = np.load(os.path.join(ROOT, "tests", "golden", "barrsmith_hotpath_input.npz"))
+    p32 = g["pts"].astype(np.float32)
+    res = cv2.FlannBasedMatcher().radiusMatch(p32, p32, 200.0)
+    lens = np.array([len(r) for r in res])
+    assert lens.max() <= 32 and 28.0 <= lens.mean() <= 32.0            # the checks = 32 cap
+    off, adj = mh.capi.neighbourhood(g["pts"], 200.0, 0)                # the full ball, for scale
+    assert np.diff(off).mean() > 200
+    off, adj = mh.capi.neighbourhood(g["pts"], 200.0, 31)
+    overlap = []
+    for i, r in enumerate(res):
+        fl = {m_.trainIdx for m_ in r if m_.trainIdx != i}
+        if fl:
+            overlap.append(len(fl & set(adj[off[i]:off[i + 1]].tolist())) / len(fl))
+    assert np.mean(overlap) > 0.6, np.mean(overlap)
+
+
 @pytest.mark.parametrize("radius", [0.0, 15.0, 40.0])
 def test_alpha_expansion_equals_reference_gco(mh, orc, radius):
     """Same dense costs + same graph => our host alpha-expansion returns the reference GCO's labels bit for bit."""
