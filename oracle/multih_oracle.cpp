@@ -15,7 +15,9 @@
 // restatement is therefore pinned by (1) tests/golden/*.npz, produced by
 // tests/golden/make_golden.py — an independent line-by-line transliteration of
 // the same reference functions on top of the real OpenCV numerical routines
-// (cv2.eigen, cv2.invert(DECOMP_SVD), cv2 4.13; the reference pins 3.1.0),
+// (cv2.eigen, cv2.invert(DECOMP_SVD), cv2 4.13; the reference pins 3.1.0), including numpy / Python-list
+// transliterations of MeanShiftClustering::Cluster (golden_meanshift.npz) and HomographyCompatibilityCheck
+// (golden_compat.npz) with the MSVC rand(),
 // (2) analytic known-answer tests (noise-free plane => generating H),
 // (3) the integer cost constants 4901 / 9802 / 0..200 at default parameters,
 // (4) the reference's own alpha-expansion compiled in place (oracle/_ref) and
