@@ -492,6 +492,7 @@ mh_status launch_cost_argmin_tc(mh_ctx* ctx, const float4* d_pts, int64_t N, con
     return cnt ? launch_tc<true, WARPS, MINB, PB, CH, PIPE, ##__VA_ARGS__>(ctx, d_pts, N, d_hyp, K, cp, fo)      \
                : launch_tc<false, WARPS, MINB, PB, CH, PIPE, ##__VA_ARGS__>(ctx, d_pts, N, d_hyp, K, cp, fo);
   switch (config) {   // (warps per CTA, CTAs per SM, 16-row blocks per warp, hypotheses per chunk, explicit pipeline)
+#ifdef MH_TUNING
     TC_CASE(30, 8, 3, 2, 256, false)
     TC_CASE(31, 8, 2, 2, 256, true)
     TC_CASE(32, 4, 6, 2, 128, false)
@@ -512,10 +513,12 @@ mh_status launch_cost_argmin_tc(mh_ctx* ctx, const float4* d_pts, int64_t N, con
     // v7: deferred candidate queue (last argument = drain threshold)
     TC_CASE(50, 4, 7, 2, 128, false, 24)
     TC_CASE(51, 4, 8, 2, 128, false, 24)
-    TC_CASE(52, 4, 6, 2, 128, false, 24)
     TC_CASE(53, 8, 3, 2, 256, false, 24)
     TC_CASE(54, 8, 4, 2, 128, false, 24)
+#endif
+    TC_CASE(52, 4, 6, 2, 128, false, 24)
     TC_CASE(55, 4, 5, 3, 128, false, 24)
+#ifdef MH_TUNING
     TC_CASE(56, 4, 4, 4, 128, false, 24)
     TC_CASE(57, 4, 4, 4, 256, false, 24)
     TC_CASE(58, 8, 2, 4, 512, false, 24)
@@ -525,6 +528,7 @@ mh_status launch_cost_argmin_tc(mh_ctx* ctx, const float4* d_pts, int64_t N, con
     TC_CASE(62, 8, 3, 3, 256, false, 24)
     TC_CASE(63, 4, 8, 2, 128, false, 32)
     TC_CASE(64, 4, 8, 2, 64, false, 24)
+#endif
     default: return fail(ctx, MH_EINVAL, "unknown tensor-core fast-path config");
   }
 #undef TC_CASE

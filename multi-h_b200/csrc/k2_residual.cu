@@ -420,6 +420,7 @@ cost_argmin_kernel(const float4* __restrict__ pts, long long N, const float* __r
   }
 }
 
+#ifdef MH_TUNING   // superseded K2 generations v4 (transposed tile) and v5 (first mma.sync kernel): tuning builds only (make TUNING=1)
 // ----------------------------------------------------------------------------
 // v4 "transposed" register tile: each thread keeps HP hypothesis PAIRS in registers (18 regs per pair) and the CTA's
 // correspondence tile lives in shared memory, read with warp-uniform (broadcast) LDS — per correspondence one LDS.128
@@ -781,6 +782,7 @@ cost_argmin_mma_kernel(const float4* __restrict__ pts, long long N, const float*
       }
   }
 }
+#endif  // MH_TUNING
 
 __global__ void fused_init_kernel(long long N, int K, int32_t* list_count, u64* best, int32_t* inlier_count,
                                   u64 best_init) {
@@ -839,6 +841,7 @@ mh_status launch_cost_fused(mh_ctx* ctx, const float4* d_pts, int64_t N, const f
       else kernel_nocnt<<<gridf, threads, 0, ctx->stream>>>(d_pts, N, d_hyp, K, kpb, cp, fo, ks > 1);
       return MH_OK;
     };
+#ifdef MH_TUNING
     auto launch_t = [&](auto kernel_cnt, auto kernel_nocnt, int threads, int hyp_per_block, int pt) -> mh_status {
       const int npairs = (K + 1) / 2;
       MH_TRY(ensure_scratch(ctx, sizeof(u64) * 10 * (uint64_t)npairs));
@@ -857,7 +860,6 @@ mh_status launch_cost_fused(mh_ctx* ctx, const float4* d_pts, int64_t N, const f
       else kernel_nocnt<<<gridf, threads, 0, ctx->stream>>>(d_pts, N, d_pairs, K, kpb, cp, fo, ks > 1);
       return MH_OK;
     };
-    if (K >= 65535 || cp.cost_outlier > 0xffff) g_fast_config = std::min(g_fast_config, 6);  // v4 packs (cost, label) in 32 bits
     auto launch_m = [&](auto kernel_cnt, auto kernel_nocnt, int pb) -> mh_status {
       const int tile = (MMA_THREADS / 32) * 16 * pb;
       const unsigned tiles_f = (unsigned)((N + tile - 1) / tile);
@@ -878,8 +880,11 @@ mh_status launch_cost_fused(mh_ctx* ctx, const float4* d_pts, int64_t N, const f
       }
       return MH_OK;
     };
+#endif
+    if (K >= 65535 || cp.cost_outlier > 0xffff) g_fast_config = std::min(g_fast_config, 6);  // the tensor-core kernel packs (cost, label) in 32 bits
     if (g_fast_config >= 30 && g_fast_config < 100) return launch_cost_argmin_tc(ctx, d_pts, N, d_hyp, K, cp, fo, g_fast_config);
     switch (g_fast_config) {
+#ifdef MH_TUNING
       case 20: MH_TRY(launch_m(cost_argmin_mma_kernel<true, 2, 2>, cost_argmin_mma_kernel<false, 2, 2>, 2)); break;
       case 21: MH_TRY(launch_m(cost_argmin_mma_kernel<true, 3, 2>, cost_argmin_mma_kernel<false, 3, 2>, 2)); break;
       case 22: MH_TRY(launch_m(cost_argmin_mma_kernel<true, 2, 4>, cost_argmin_mma_kernel<false, 2, 4>, 4)); break;
@@ -892,13 +897,16 @@ mh_status launch_cost_fused(mh_ctx* ctx, const float4* d_pts, int64_t N, const f
       case 13: launch_t(cost_argmin_t_kernel<true, 128, 3, 4, 512>, cost_argmin_t_kernel<false, 128, 3, 4, 512>, 128, 1024, 512); break;
       case 14: launch_t(cost_argmin_t_kernel<true, 256, 3, 2, 1024>, cost_argmin_t_kernel<false, 256, 3, 2, 1024>, 256, 1024, 1024); break;
       case 15: launch_t(cost_argmin_t_kernel<true, 128, 7, 2, 256>, cost_argmin_t_kernel<false, 128, 7, 2, 256>, 128, 512, 256); break;
+#endif
+#ifdef MH_TUNING
       case 0: launch(cost_argmin_kernel<true, 256, 3, 256>, cost_argmin_kernel<false, 256, 3, 256>, 256, 256); break;
       case 1: launch(cost_argmin_kernel<true, 256, 2, 256>, cost_argmin_kernel<false, 256, 2, 256>, 256, 256); break;
       case 3: launch(cost_argmin_kernel<true, 128, 5, 256>, cost_argmin_kernel<false, 128, 5, 256>, 128, 256); break;
       case 4: launch(cost_argmin_kernel<true, 128, 6, 128>, cost_argmin_kernel<false, 128, 6, 128>, 128, 128); break;
+#endif
       case 5: launch(cost_argmin_kernel<true, 128, 7, 128>, cost_argmin_kernel<false, 128, 7, 128>, 128, 128); break;
       case 6: launch(cost_argmin_kernel<true, 128, 4, 256>, cost_argmin_kernel<false, 128, 4, 256>, 128, 256); break;
-      default: launch(cost_argmin_kernel<true, 256, 4, 256>, cost_argmin_kernel<false, 256, 4, 256>, 256, 256); break;
+      default: return fail(ctx, MH_EINVAL, "unknown fast-path config (this build keeps 5, 6, 52 and 55; make TUNING=1 for the rest)");
     }
     MH_LAUNCHED(ctx, "cost_argmin_kernel");
     return MH_OK;
