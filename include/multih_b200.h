@@ -68,11 +68,22 @@ typedef struct mh_params {
   int32_t prefilter;        /* mh_process: 1 = run K0 first (MultiH.cpp:807-838: Hartley-Sturm correction, affine
                                consistency test, optimal affine) as Process() does after estimating F; dropped
                                correspondences get label -2.  0 (default) = inputs are already refined             */
-  int32_t compatibility_check; /* mh_process: 1 = finish with HomographyCompatibilityCheck (MultiH.cpp:78-86, 100-222) as
-                                  Process() does; 0 (default) = return the clusters of the alternating optimisation       */
+  int32_t compatibility_check; /* mh_process: 1 (default) = finish with HomographyCompatibilityCheck (MultiH.cpp:78-86, 100-222)
+                                  as Process() does; 0 = return the clusters of the alternating optimisation              */
 } mh_params;
 
-void mh_default_params(mh_params* p); /* main.cpp:55-59: 2.6 / 2.2 / 0.005 / 0.5 / 20 */
+/* main.cpp:55-59: 2.6 / 2.2 / 0.005 / 0.5 / 20 (the CLI's values; the class defaults of MultiH.h:7-10 are what the MultiH
+ * shims of include/multih_b200.hpp and multih_b200.MultiH pass).  Where mh_process deliberately differs from
+ * MultiH::Process(), all in one place:
+ *   - F is an input; the RANSAC of MultiH.cpp:775 and its inlier mask are upstream;
+ *   - prefilter = 0 by default (inputs already refined); the shims set 1, as Process() refines every correspondence;
+ *   - every fit returns the reference's own linear solution (do_numerical_refinement = false): the LM polish reads out of
+ *     bounds (Homography_RefineHAFCallback.h:148-151), see mh_params.lm_refine of a later revision;
+ *   - the neighbourhood is the exact 31 nearest within the radius (max_neighbours), FLANN's is a randomised 32-check search;
+ *   - K <= 1 after the loop: the reference discards everything and calls cv::findHomography (HandleDegenerateCase,
+ *     MultiH.cpp:88-94, 719-741); mh_process returns the single surviving homography with its inliers (labels 0 / -1,
+ *     MultiH.cpp:280-285, 743-768) or K_out = 0 with all labels -1 — labels_out[i] < K_out always holds. */
+void mh_default_params(mh_params* p);
 
 /* ---- context ----------------------------------------------------------- */
 mh_status mh_create(const mh_params* params, int device, mh_ctx** out); /* MultiH::MultiH  (MultiH.cpp:10-21) */

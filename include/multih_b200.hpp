@@ -12,8 +12,11 @@
 //  * F is an input: GetFundamentalMatrixAndRefineData (MultiH.cpp:770-848) is upstream of the accelerated path;
 //  * GetDestinationPoints returns the destination points (the reference returns src: MultiH.h:64);
 //  * GetHomography(idx) stays 1-based (MultiH.h:69); labels: -1 = outlier, 0..K-1 (MultiH.h:61-62);
-//  * no LM polish after the linear fits (its callbacks read out of bounds, Homography_RefineHAFCallback.h:148-151),
-//    no HomographyCompatibilityCheck / HandleDegenerateCase post-processing (out of scope of the accelerated path).
+//  * Process() runs what the reference's Process() runs after its F-RANSAC: the per-correspondence refinement / affine
+//    consistency filter (MultiH.cpp:807-838), the alternating optimisation and HomographyCompatibilityCheck (:76-86);
+//    correspondences the filter drops disappear from the getters, as in the reference (which only keeps the survivors);
+//  * no LM polish after the linear fits (its callbacks read out of bounds, Homography_RefineHAFCallback.h:148-151) and no
+//    HandleDegenerateCase (cv::findHomography): with K <= 1 the single homography's inliers are returned.
 // ============================================================================
 #pragma once
 #include <array>
@@ -40,6 +43,8 @@ class MultiH {
     params_.locality = locality;
     params_.lambda = lambda;
     params_.min_inliers = minimum_inlier_number;
+    params_.prefilter = 1;            // MultiH.cpp:807-838
+    params_.compatibility_check = 1;  // MultiH.cpp:76-86
     const mh_status st = mh_create(&params_, device, &ctx_);
     if (st != MH_OK) throw std::runtime_error("multih_b200: no usable CUDA device (there is no CPU fallback)");
   }
@@ -65,6 +70,15 @@ class MultiH {
       return false;
     }
     cluster_number_ = k;
+    // the reference's getters only know the correspondences that survived its filter (label -2 = dropped here)
+    size_t m = 0;
+    for (int i = 0; i < n; ++i)
+      if (labeling_[i] > -2) {
+        labeling_[m] = labeling_[i]; src_[m] = src_[i]; dst_[m] = dst_[i];
+        for (int k4 = 0; k4 < 4; ++k4) aff_[4 * m + k4] = aff_[4 * (size_t)i + k4];
+        ++m;
+      }
+    labeling_.resize(m); src_.resize(m); dst_.resize(m); aff_.resize(4 * m);
     return true;
   }
 #ifdef MULTIH_B200_WITH_OPENCV

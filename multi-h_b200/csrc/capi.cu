@@ -152,8 +152,8 @@ void mh_default_params(mh_params* p) {
   p->max_gc_cycles = 1000;   // MultiH.cpp:543
   p->max_neighbours = 31;    // FLANN default SearchParams: checks = 32 (query included)
   p->precise_pipeline = 1;
-  p->prefilter = 0;
-  p->compatibility_check = 0;
+  p->prefilter = 0;            // inputs are taken as already refined; the MultiH class shims switch it on (Process() takes raw rows)
+  p->compatibility_check = 1;  // Process() always ends with HomographyCompatibilityCheck when K > 1 (MultiH.cpp:76-86)
 }
 
 mh_status mh_create(const mh_params* params, int device, mh_ctx** out) {

@@ -500,16 +500,30 @@ static void eval_move(const MoveProblem& P, const int32_t* lab, int alpha, MoveW
 // ---------------------------------------------------------------------------
 class MovePool {
  public:
+  static std::mutex& global_mutex() { static std::mutex gm; return gm; }
+  static MovePool*& instance() { static MovePool* pool = nullptr; return pool; }
+  // joins the workers; called when the library is unloaded (dlclose / process exit), see mh_movepool_shutdown below
+  static void shutdown() {
+    std::lock_guard<std::mutex> lk(global_mutex());
+    MovePool*& pool = instance();
+    if (!pool || pool->owner_ != getpid()) return;   // (a forked child never owned the threads)
+    { std::lock_guard<std::mutex> l2(pool->m_); pool->quit_ = true; pool->session_ = true; }
+    pool->cv_.notify_all();
+    pool->epoch_.fetch_add(2);
+    for (std::thread& t : pool->th_) t.join();
+    delete pool;
+    pool = nullptr;
+  }
   static MovePool* acquire() {   // nullptr: no threads wanted / pool busy
-    static std::mutex gm;
-    static MovePool* pool = nullptr;
+    std::mutex& gm = global_mutex();
+    MovePool*& pool = instance();
     static pid_t owner = 0;
     std::lock_guard<std::mutex> lk(gm);
     int want = (int)std::thread::hardware_concurrency();
     if (const char* e = std::getenv("MH_GC_THREADS")) want = std::atoi(e);
     want = std::min(want, 8);   // measured on the 16-core B200 host: 8 -> 16 threads gains 2 %
     if (want < 2) return nullptr;
-    if (!pool || owner != getpid()) { pool = new MovePool(want - 1); owner = getpid(); }   // (a forked child leaks the parent's)
+    if (!pool || owner != getpid()) { pool = new MovePool(want - 1); owner = getpid(); pool->owner_ = owner; }   // (a forked child leaks the parent's)
     if (pool->busy_) return nullptr;
     pool->busy_ = true;
     pool->begin_session();
@@ -568,8 +582,10 @@ class MovePool {
       {
         std::unique_lock<std::mutex> lk(m_);
         cv_.wait(lk, [this] { return session_; });
+        if (quit_) return;
       }
       for (;;) {   // inside a session: spin on the epoch
+        if (quit_) return;
         const uint64_t e = epoch_.load();
         if (e != seen && (e & 1) == 0) {
           active_.fetch_add(1);
@@ -590,12 +606,17 @@ class MovePool {
   std::mutex m_;
   std::condition_variable cv_;
   bool session_ = false;
+  std::atomic<bool> quit_{false};
+  pid_t owner_ = 0;
   std::atomic<bool> busy_{false};
   std::function<void(int, int)> fn_;
   int njobs_ = 0;
   std::atomic<int> next_{0}, done_{0}, active_{0};
   std::atomic<uint64_t> epoch_{0};
 };
+
+// the worker threads must not outlive the library's code: join them when it is unloaded
+__attribute__((destructor)) static void mh_movepool_shutdown() { MovePool::shutdown(); }
 
 // The neighbourhood is the same for every labelling step of a pair (MultiH.cpp:231-253 builds it once), so the symmetrised
 // graph is kept between calls: one entry per thread, keyed on the content of the caller's CSR.

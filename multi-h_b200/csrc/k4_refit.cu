@@ -520,6 +520,7 @@ compat_trial_kernel(const double* __restrict__ pts64, const int32_t* __restrict_
   __shared__ double sH[9];
   const int c = blockIdx.y, t = blockIdx.x, tid = threadIdx.x;
   const int beg = moff[c], end = moff[c + 1], n = end - beg - 3;
+  if (n > P) return;   // more members than fit the shared-memory sort: compat_trial_big_kernel's share
   const int32_t* sm = samples + ((size_t)c * trials + t) * 3;
   const int s0 = sm[0], s1 = sm[1], s2 = sm[2];
   if (tid == 0) {
@@ -595,17 +596,173 @@ compat_trial_kernel(const double* __restrict__ pts64, const int32_t* __restrict_
   }
 }
 
+// The same statistics for clusters too large to sort in shared memory (the reference has no size limit): nothing is stored —
+// every pass recomputes the transfer errors.  The value at sorted index lo = n/2 - 3 is found by an 8-bit radix select over the
+// errors' bit patterns (non-negative doubles order like unsigned integers; 8 passes), one more pass collects what else is
+// needed: how many errors lie below / at that value, the five smallest above it and the three largest of all.
+constexpr int COMPAT_SMEM_MAX_N = 16384;
+__global__ void __launch_bounds__(COMPAT_THREADS)
+compat_trial_big_kernel(const double* __restrict__ pts64, const int32_t* __restrict__ members, const int32_t* __restrict__ moff,
+                        const int32_t* __restrict__ samples /*[T][trials][3]*/, int trials, HafGeom g,
+                        double* __restrict__ out /*[T][trials][8]*/) {
+  __shared__ double sH[9];
+  __shared__ unsigned hist[256];
+  __shared__ unsigned long long s_prefix;
+  __shared__ unsigned s_rank;
+  __shared__ unsigned long long s_small[COMPAT_THREADS][5], s_large[COMPAT_THREADS][3];
+  __shared__ unsigned s_less, s_eq;
+  const int c = blockIdx.y, t = blockIdx.x, tid = threadIdx.x;
+  const int beg = moff[c], end = moff[c + 1], n = end - beg - 3;
+  if (n <= COMPAT_SMEM_MAX_N) return;   // compat_trial_kernel's share
+  const int32_t* sm = samples + ((size_t)c * trials + t) * 3;
+  const int s0 = sm[0], s1 = sm[1], s2 = sm[2];
+  if (tid == 0) {
+    double p1[3][2], p2[3][2];
+    const int si[3] = {s0, s1, s2};
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const double* q = pts64 + 4 * (size_t)si[k];
+      p1[k][0] = q[0]; p1[k][1] = q[1]; p2[k][0] = q[2]; p2[k][1] = q[3];
+    }
+    Norm2 nm;   // NormalizePoints (3PTcb.h:146-197) on the three pairs
+    nm.mx1 = (p1[0][0] + p1[1][0] + p1[2][0]) / 3.0; nm.my1 = (p1[0][1] + p1[1][1] + p1[2][1]) / 3.0;
+    nm.mx2 = (p2[0][0] + p2[1][0] + p2[2][0]) / 3.0; nm.my2 = (p2[0][1] + p2[1][1] + p2[2][1]) / 3.0;
+    double d1 = 0, d2 = 0;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      d1 += sqrt((p1[k][0] - nm.mx1) * (p1[k][0] - nm.mx1) + (p1[k][1] - nm.my1) * (p1[k][1] - nm.my1));
+      d2 += sqrt((p2[k][0] - nm.mx2) * (p2[k][0] - nm.mx2) + (p2[k][1] - nm.my2) * (p2[k][1] - nm.my2));
+    }
+    nm.s1 = sqrt(2.0) / (d1 / 3.0);
+    nm.s2 = sqrt(2.0) / (d2 / 3.0);
+    double Fn[9], ex, ey;
+    normalised_F_and_epipole(g, nm, Fn, ex, ey);
+    double Nq[6] = {0, 0, 0, 0, 0, 0}, r[3] = {0, 0, 0};
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+      rows_3pt((p1[k][0] - nm.mx1) * nm.s1, (p1[k][1] - nm.my1) * nm.s1, (p2[k][0] - nm.mx2) * nm.s2,
+               (p2[k][1] - nm.my2) * nm.s2, ex, ey, Fn, Nq, r);
+    double h3[3], H[9];
+    pinv_normal3(Nq, r, h3);
+    __align__(16) float unused[12];
+    assemble_3pt_and_store(h3, Fn, ex, ey, nm, g, unused, H);
+#pragma unroll
+    for (int k = 0; k < 9; ++k) sH[k] = H[k];
+    s_prefix = 0ull;
+    s_rank = (unsigned)max(0, n / 2 - 3);
+  }
+  __syncthreads();
+  double h[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) h[k] = sH[k];
+  const unsigned long long inf_bits = 0x7ff0000000000000ull;
+  auto key_of = [&](int j, bool& live) {   // bit pattern of member j's squared transfer error (the same arithmetic as above)
+    const int idx = members[j];
+    live = !(idx == s0 || idx == s1 || idx == s2);
+    const double* q = pts64 + 4 * (size_t)idx;
+    const double s = h[6] * q[0] + h[7] * q[1] + h[8];
+    const double x1 = (h[0] * q[0] + h[1] * q[1] + h[2]) / s, y1 = (h[3] * q[0] + h[4] * q[1] + h[5]) / s;
+    const double dx = q[2] - x1, dy = q[3] - y1;
+    const double d = dx * dx + dy * dy;
+    return d == d ? (unsigned long long)__double_as_longlong(d) : inf_bits;   // NaN sorts last, as +inf
+  };
+  for (int shift = 56; shift >= 0; shift -= 8) {
+    hist[tid] = 0;
+    __syncthreads();
+    const unsigned long long prefix = s_prefix;
+    for (int j = beg + tid; j < end; j += COMPAT_THREADS) {
+      bool live;
+      const unsigned long long k = key_of(j, live);
+      if (live && (shift == 56 || (k >> (shift + 8)) == (prefix >> (shift + 8)))) atomicAdd(&hist[(unsigned)(k >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    if (tid == 0) {
+      unsigned r = s_rank, b = 0;
+      while (r >= hist[b]) { r -= hist[b]; ++b; }
+      s_rank = r;
+      s_prefix = prefix | ((unsigned long long)b << shift);
+    }
+    __syncthreads();
+  }
+  const unsigned long long klo = s_prefix;   // the error at sorted index max(0, n/2 - 3)
+  unsigned long long small[5] = {~0ull, ~0ull, ~0ull, ~0ull, ~0ull}, large[3] = {0ull, 0ull, 0ull};
+  unsigned less = 0, eq = 0, nlarge = 0;
+  for (int j = beg + tid; j < end; j += COMPAT_THREADS) {
+    bool live;
+    const unsigned long long k = key_of(j, live);
+    if (!live) continue;
+    less += k < klo;
+    eq += k == klo;
+    if (k > klo && k < small[4]) {   // keep the five smallest above klo, ascending, duplicates included
+      small[4] = k;
+#pragma unroll
+      for (int a = 4; a > 0; --a)
+        if (small[a] < small[a - 1]) { const unsigned long long x = small[a]; small[a] = small[a - 1]; small[a - 1] = x; }
+    }
+    if (nlarge < 3 || k > large[2]) {   // and the three largest of all, descending
+      large[2] = k;
+      nlarge = min(nlarge + 1, 3u);
+#pragma unroll
+      for (int a = 2; a > 0; --a)
+        if (large[a] > large[a - 1]) { const unsigned long long x = large[a]; large[a] = large[a - 1]; large[a - 1] = x; }
+    }
+  }
+  if (tid == 0) { s_less = 0; s_eq = 0; }
+  __syncthreads();
+  atomicAdd(&s_less, less);
+  atomicAdd(&s_eq, eq);
+#pragma unroll
+  for (int a = 0; a < 5; ++a) s_small[tid][a] = small[a];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) s_large[tid][a] = large[a];
+  __syncthreads();
+  if (tid == 0) {
+    unsigned long long S5[5] = {~0ull, ~0ull, ~0ull, ~0ull, ~0ull}, L3[3] = {0ull, 0ull, 0ull};
+    for (int w = 0; w < COMPAT_THREADS; ++w) {
+      for (int a = 0; a < 5; ++a) {
+        const unsigned long long k = s_small[w][a];
+        if (k < S5[4]) {
+          S5[4] = k;
+          for (int e = 4; e > 0; --e)
+            if (S5[e] < S5[e - 1]) { const unsigned long long x = S5[e]; S5[e] = S5[e - 1]; S5[e - 1] = x; }
+        }
+      }
+      for (int a = 0; a < 3; ++a) {   // every thread saw >= 3 live members (n > COMPAT_SMEM_MAX_N), so all slots are real
+        const unsigned long long k = s_large[w][a];
+        if (k > L3[2]) {
+          L3[2] = k;
+          for (int e = 2; e > 0; --e)
+            if (L3[e] > L3[e - 1]) { const unsigned long long x = L3[e]; L3[e] = L3[e - 1]; L3[e - 1] = x; }
+        }
+      }
+    }
+    double* o = out + ((size_t)c * trials + t) * 8;
+    const int m = n / 2, lo = max(0, m - 3), hi = min(n - 1, m + 1);
+    for (int k = 0; k < 5; ++k) {
+      const unsigned rank = (unsigned)(lo + k);
+      unsigned long long v = inf_bits;
+      if (lo + k <= hi) v = rank < s_less + s_eq ? klo : S5[rank - s_less - s_eq];
+      o[k] = __longlong_as_double((long long)v);
+    }
+    for (int k = 0; k < 3; ++k) o[5 + k] = __longlong_as_double((long long)L3[k]);
+  }
+}
+
 mh_status launch_compat_trials(mh_ctx* ctx, const double* d_pts64, const int32_t* d_members, const int32_t* d_moff,
                                const int32_t* d_samples, int T, int trials, int max_n, double* d_out) {
   if (T <= 0) return MH_OK;
   int P = 2;
-  while (P < max_n) P <<= 1;
+  while (P < std::min(max_n, COMPAT_SMEM_MAX_N)) P <<= 1;
   const size_t smem = (size_t)P * sizeof(double);
-  if (smem > 200 * 1024) return fail(ctx, MH_EINVAL, "mh_compatibility_check: a cluster has more than 25600 members");
   MH_CUDA(ctx, cudaFuncSetAttribute(compat_trial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   compat_trial_kernel<<<dim3((unsigned)trials, (unsigned)T), COMPAT_THREADS, smem, ctx->stream>>>(
       d_pts64, d_members, d_moff, d_samples, trials, P, haf_geom(ctx), d_out);
   MH_LAUNCHED(ctx, "compat_trial_kernel");
+  if (max_n > COMPAT_SMEM_MAX_N) {
+    compat_trial_big_kernel<<<dim3((unsigned)trials, (unsigned)T), COMPAT_THREADS, 0, ctx->stream>>>(
+        d_pts64, d_members, d_moff, d_samples, trials, haf_geom(ctx), d_out);
+    MH_LAUNCHED(ctx, "compat_trial_big_kernel");
+  }
   return MH_OK;
 }
 

@@ -5,8 +5,8 @@
 // with MergingStep (:352-471) and LabelingStep (:513-602), driving the K1-K4
 // kernels and the host alpha-expansion.  F is an input (north star), so
 // GetFundamentalMatrixAndRefineData (:770-848) is the caller's business, and the
-// post-processing HomographyCompatibilityCheck / HandleDegenerateCase
-// (:100-222, :719-741) is out of scope.  The reference's
+// HandleDegenerateCase (:719-741, OpenCV's RANSAC findHomography) stays with the caller;
+// HomographyCompatibilityCheck (:100-222) runs at the end when params.compatibility_check is set.  The reference's
 // Levenberg-Marquardt polish after each linear fit is not reproduced (its
 // callbacks read out of bounds): every fit returns the
 // reference's own linear solution (do_numerical_refinement = false).
@@ -417,15 +417,21 @@ mh_status mh_process(mh_ctx* ctx, const double* pts, const double* aff, const do
     }
     if (changed) not_changed_number = 0; else ++not_changed_number;
 
-    if (K == 1) {  // MultiH.cpp:280-285
+    if (K == 1) {  // MultiH.cpp:280-285: ComputeInliersOfHomography(0) (:743-768)
+      // The reference leaves the labels of the previous labelling step in place here, but then (K <= 1, MultiH.cpp:88-94) clears
+      // them all and falls back to cv::findHomography.  That fallback is the caller's; what is returned is the one homography
+      // with its inliers: every other label is -1, so that labels < K_out.
       MH_TRY(upload_hyps(1));
+      std::fill(labeling.begin(), labeling.end(), -1);
       MH_TRY(mh_memcpy_h2d(ctx, b_labels.p, labeling.data(), sizeof(int32_t) * (size_t)N));
       if (precise) MH_TRY(launch_inliers_of64(ctx, pts64, N, b_hyp64.as<double>(), 0, b_labels.as<int32_t>()));
       else MH_TRY(mh_inliers_of_homography(ctx, b_pts.p, N, b_hyp.p, 0, b_labels.p));
       MH_TRY(mh_memcpy_d2h(ctx, labeling.data(), b_labels.p, sizeof(int32_t) * (size_t)N));
       break;
-    } else if (K == 0)
+    } else if (K == 0) {
+      std::fill(labeling.begin(), labeling.end(), -1);
       break;
+    }
 
     // -- LabelingStep (MultiH.cpp:513-602)
     const int L = K + 1;

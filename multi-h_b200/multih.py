@@ -3,7 +3,9 @@ method names and return conventions, forwarding to the C ABI (mh_process).  Diff
   * F is an input (`Process(src, dst, affines, F)`): GetFundamentalMatrixAndRefineData (MultiH.cpp:770) is upstream of
     the hot path;
   * GetDestinationPoints returns the destination points (the reference returns src, MultiH.h:64 — a bug);
-  * GetHomography stays 1-based like the reference (MultiH.h:69).
+  * GetHomography stays 1-based like the reference (MultiH.h:69);
+  * like the reference's Process(), the per-correspondence refinement filter (MultiH.cpp:807-838) and the final
+    HomographyCompatibilityCheck (:76-86) run; the getters only know the correspondences that survive the filter.
 """
 from __future__ import annotations
 
@@ -16,7 +18,7 @@ class MultiH:
     def __init__(self, thr_fund_mat=3.0, thr_hom=2.5, locality=0.002, lambda_=0.5, minimum_inlier_number=0, device=0):
         # defaults: MultiH.h:7-10, 49-53
         self._params = capi.default_params(thr_fundamental=thr_fund_mat, thr_homography=thr_hom, locality=locality,
-                                           lambda_=lambda_, min_inliers=minimum_inlier_number)
+                                           lambda_=lambda_, min_inliers=minimum_inlier_number, prefilter=1, compatibility_check=1)
         self._device = device
         self._ctx = None
         self._labels = np.zeros(0, dtype=np.int32)
@@ -32,8 +34,9 @@ class MultiH:
             return False
         if self._ctx is None:
             self._ctx = capi.Context(self._params, self._device)
-        self._src, self._dst, self._aff = src, dst, aff
-        self._labels, self._H, _ = self._ctx.process(np.concatenate([src, dst], axis=1), aff, F)
+        labels, self._H, _ = self._ctx.process(np.concatenate([src, dst], axis=1), aff, F)
+        kept = labels > -2   # -2 = dropped by the refinement filter: the reference forgets those correspondences
+        self._src, self._dst, self._aff, self._labels = src[kept], dst[kept], aff[kept], labels[kept]
         return True
 
     def GetLabel(self, idx): return int(self._labels[idx])

@@ -32,7 +32,7 @@ def oracle_process(pts, aff, F, thr=2.2, locality=0.005, lam=0.5, straightness=0
         trace["K0"] = len(hyp)
     off, adj = orc.radius_neighbours(pts, 1.0 / locality, max_neighbours)                 # :231-253
     labeling = np.full(N, -1, dtype=np.int32)
-    last_energy, not_changed, it, energy_final = float(2 ** 31 - 1), 0, 0, 0.0
+    last_energy, not_changed, it, energy_final, k1_exit = float(2 ** 31 - 1), 0, 0, 0.0, False
     potts = orc.smooth_cost(0, 1, lam)
     if expansion is None:
         expansion = (lambda c, o, a, init: orc.gco_ref_expansion(c, potts, o, a, init, max_gc_cycles))
@@ -51,10 +51,12 @@ def oracle_process(pts, aff, F, thr=2.2, locality=0.005, lam=0.5, straightness=0
                 hyp = merged
         not_changed = 0 if changed else not_changed + 1
         K = len(hyp)
-        if K == 1:                                                           # :280-285
-            labeling = orc.inliers_of_homography(pts, hyp[0], thr, 0, labeling)
+        if K == 1:                                                           # :280-285; the stale labels of earlier steps are
+            k1_exit = True                                                   # dropped as Process() does right after (:88-94)
+            labeling = orc.inliers_of_homography(pts, hyp[0], thr, 0, np.full(N, -1, dtype=np.int32))
             break
         if K == 0:
+            labeling = np.full(N, -1, dtype=np.int32)
             break
         cost = orc.data_cost_dense(pts, hyp, lam, thr, threads=8)           # LabelingStep :513-543
         init = None if changed else np.clip(labeling + 1, 0, K)
@@ -73,4 +75,4 @@ def oracle_process(pts, aff, F, thr=2.2, locality=0.005, lam=0.5, straightness=0
         full = np.full(len(keepmask), -2, dtype=np.int32)
         full[keepmask] = labeling
         labeling = full
-    return labeling, hyp, dict(iterations=it - 1, energy=energy_final)  # final_iteration_number, MultiH.cpp:311
+    return labeling, hyp, dict(iterations=it - 1, energy=energy_final, k1_exit=k1_exit)  # final_iteration_number, MultiH.cpp:311

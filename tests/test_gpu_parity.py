@@ -6,7 +6,8 @@ each assert:
   * K2 residuals        : |d2_gpu - d2_ref| <= 5e-3 px^2 for d2 < 100 px^2 (FP32 evaluation in normalised coordinates)
   * K2 integer costs    : exact match >= 99.9 %, every mismatch |delta| == 1 except threshold flips (< 1e-5 of entries)
   * K3 mean-shift       : same number of trajectories / window iterations / centres as the oracle, centres within 1e-6
-  * labels              : agreement with the oracle pipeline (reference GCO) reported, >= 95 % required
+  * labels              : mh_process (default FP64 data path) == the oracle pipeline with the reference's own GCO: same number of
+                          clusters and 100 % label agreement on the bundled pair and the synthetic scenes (asserted)
 """
 import os
 
@@ -284,9 +285,9 @@ def test_k3_meanshift_and_k4_3pt_vs_oracle(mh, orc):
     d_pts, d_aff = ctx.upload(sc.pts, sc.aff)
     fo = orc.features10(orc.haf_hypotheses(sc.pts, sc.aff, sc.F), sc.pts, 0.005)
     cen, asg, st = ctx.meanshift(torch.from_numpy(fo).cuda(), 2.2)
-    co, ao, _, sto = orc.meanshift(fo, 2.2)
+    co, ao, rng1, sto = orc.meanshift(fo, 2.2)
     assert st == sto and cen.shape[0] == co.shape[0]            # same trajectories / window iterations / centres
-    assert np.abs(cen.cpu().numpy() - co).max() <= 1e-6
+    assert np.abs(cen.cpu().numpy() - co).max() <= 1e-6 and ctx.rng_state == rng1
     agree = (asg.cpu().numpy() == ao).mean()
     assert agree >= 0.999, agree
     # 6-D (MergingStep) on cluster homographies + L2 metric variant runs
@@ -295,14 +296,37 @@ def test_k3_meanshift_and_k4_3pt_vs_oracle(mh, orc):
     order = np.argsort(ao, kind="stable"); order = order[ao[order] >= 0]
     offs = np.concatenate([[0], np.cumsum(np.bincount(ao[ao >= 0], minlength=C))]).astype(np.int32)
     H3o, keep_o = orc.cluster_3pt(sc.pts, offs, order.astype(np.int32), sc.F)
-    if agree == 1.0:
-        assert np.array_equal(keep.cpu().numpy().astype(bool), keep_o)
-        rel = _rel(ctx.hypotheses_to_host(d_h3)[keep_o], H3o[keep_o])
-        assert np.percentile(rel, 95) <= 1e-4, np.percentile(rel, [50, 95, 100])
+    # the cluster fit is compared on the clusters whose member sets are identical (all of them when agree == 1)
+    ag = asg.cpu().numpy()
+    same = np.array([np.array_equal(np.where(ag == c)[0], np.where(ao == c)[0]) for c in range(C)])
+    assert same.mean() >= 0.99
+    assert np.array_equal(keep.cpu().numpy().astype(bool)[same], keep_o[same])
+    sel = same & keep_o
+    rel = _rel(ctx.hypotheses_to_host(d_h3)[sel], H3o[sel])
+    assert np.percentile(rel, 95) <= 1e-4, np.percentile(rel, [50, 95, 100])
+    # 6-D (MergingStep, MultiH.cpp:397) on the cluster homographies
     f6 = orc.features6(H3o[keep_o])
     cen6, asg6, st6 = ctx.meanshift(torch.from_numpy(f6).cuda(), 2.2)
-    
-    assert cen6.shape[1] == 6 and cen6.shape[0] >= 1
+    c6o, a6o, _, st6o = orc.meanshift(f6, 2.2, rng_state=rng1)   # the seed generator's state carries over, as rand() does
+    assert st6 == st6o and cen6.shape == c6o.shape and np.abs(cen6.cpu().numpy() - c6o).max() <= 1e-6
+    assert np.array_equal(asg6.cpu().numpy(), a6o)
+
+
+def test_k3_meanshift_l2_metric_vs_oracle(mh, orc):
+    """meanshift_metric = 1: the same sequential algorithm with the window sum_j d_j^2 < bw^2 (exact FP64 member; the oracle's
+    metric = 1) — trajectories, iterations, centres and assignments as the oracle's."""
+    import torch
+
+    sc = mh.scenes.make_scene(3000, 6, seed=7)
+    fo = orc.features10(orc.haf_hypotheses(sc.pts, sc.aff, sc.F), sc.pts, 0.005)
+    ctx = mh.Context(mh.capi.default_params(meanshift_metric=1))
+    cen, asg, st = ctx.meanshift(torch.from_numpy(fo).cuda(), 2.2)
+    co, ao, _, sto = orc.meanshift(fo, 2.2, metric=1)
+    assert st == sto and cen.shape[0] == co.shape[0], (st, sto)
+    assert np.abs(cen.cpu().numpy() - co).max() <= 1e-6
+    assert (asg.cpu().numpy() == ao).mean() >= 0.999
+    c0, _, _, st0 = orc.meanshift(fo, 2.2, metric=0)
+    assert st != st0   # the two windows really differ on this input
 
 
 def test_k3_meanshift_cooperative_path_vs_oracle(mh, orc):
@@ -439,13 +463,13 @@ def test_pipeline_labels_vs_oracle(mh, orc):
     params = mh.capi.default_params(locality=1 / 20.0)
     ctx = mh.Context(params)
     lab, H, K = ctx.process(sc.pts, sc.aff, sc.F)
-    lab_o, H_o, info = oracle_process(sc.pts, sc.aff, sc.F, locality=1 / 20.0)
+    lab_o, H_o, info = oracle_process(sc.pts, sc.aff, sc.F, locality=1 / 20.0, compatibility_check=True)
     agree, ari = (lab == lab_o).mean(), _ari(lab, lab_o)
     print(f"\n[parity] synthetic 3000x6: K gpu={K} oracle={len(H_o)} label agreement={agree:.4f} ARI={ari:.4f} "
           f"iterations gpu={ctx.iterations} oracle={info['iterations']} outliers gpu={(lab < 0).mean():.3f} "
           f"oracle={(lab_o < 0).mean():.3f}")
-    assert abs(K - len(H_o)) <= 1
-    assert ari >= 0.9
+    assert K == len(H_o) and agree == 1.0 and ctx.iterations == info["iterations"]
+    assert np.abs(H / H[:, 8:9] - H_o / H_o[:, 8:9]).max() <= 1e-6
     # the FP32 throughput data path runs the same control flow; it is compared as a clustering only (chaotic loop)
     ctx32 = mh.Context(mh.capi.default_params(locality=1 / 20.0, precise_pipeline=0))
     lab32, H32, K32 = ctx32.process(sc.pts, sc.aff, sc.F)
@@ -460,14 +484,13 @@ def test_pipeline_bundled_pair(mh, orc):
     g = np.load(os.path.join(GOLD, "barrsmith_hotpath_input.npz"))
     ctx = mh.Context()
     lab, H, K = ctx.process(g["pts"], g["aff"], g["F"])
-    lab_o, H_o, info = oracle_process(g["pts"], g["aff"], g["F"])
+    lab_o, H_o, info = oracle_process(g["pts"], g["aff"], g["F"], compatibility_check=True)
     agree, ari = (lab == lab_o).mean(), _ari(lab, lab_o)
     big = np.bincount(lab[lab >= 0]).max() / len(lab)
     print(f"\n[parity] barrsmith N={len(lab)}: K gpu={K} oracle={len(H_o)} label agreement={agree:.4f} ARI={ari:.4f} "
           f"largest plane gpu={big:.3f} outliers gpu={(lab < 0).mean():.3f} oracle={(lab_o < 0).mean():.3f} "
           f"stages={ctx.stage_ms()}")
-    assert abs(K - len(H_o)) <= 1
-    assert ari >= 0.9
+    assert K == len(H_o) and agree == 1.0 and ctx.iterations == info["iterations"]
     assert 0.35 <= big <= 0.6   # the largest plane of the shipped result holds ~47 % of the kept points
 
 
@@ -595,11 +618,11 @@ def test_pipeline_from_raw_correspondences(mh, orc):
     pts, aff = g["barr_pts"][inl], g["barr_aff"][inl]
     ctx = mh.Context(mh.capi.default_params(prefilter=1))
     lab, H, K = ctx.process(pts, aff, F)
-    lab_o, H_o, info = oracle_process(pts, aff, F, prefilter=True)
+    lab_o, H_o, info = oracle_process(pts, aff, F, prefilter=True, compatibility_check=True)
     agree = (lab == lab_o).mean()
     print(f"\n[parity] raw barrsmith N={len(pts)} kept={int((lab > -2).sum())}: K gpu={K} oracle={len(H_o)} agreement={agree:.4f}")
     assert np.array_equal(lab == -2, lab_o == -2)
-    assert K == len(H_o) and agree >= 0.99
+    assert K == len(H_o) and agree == 1.0
 
 
 def test_multih_class_surface(mh):
@@ -607,5 +630,104 @@ def test_multih_class_surface(mh):
     o = mh.MultiH(2.6, 2.2, 0.005, 0.5, 20)
     assert not o.Process(g["pts"][:5, :2], g["pts"][:5, 2:], g["aff"][:5], g["F"])   # < 8 points: MultiH.cpp:44-50
     assert o.Process(g["pts"][:, :2], g["pts"][:, 2:], g["aff"], g["F"])
-    assert o.GetPointNumber() == len(g["pts"]) and o.GetClusterNumber() >= 1
+    assert 0.9 * len(g["pts"]) <= o.GetPointNumber() <= len(g["pts"]) and o.GetClusterNumber() >= 1   # survivors of the filter
     assert o.GetHomography(1).shape == (3, 3) and o.GetLabels().min() >= -1
+
+
+def test_k2_single_homography_inliers_vs_oracle(gpu_ctx, dev, scene, orc):
+    """a9: ComputeInliersOfHomography (MultiH.cpp:743-768) — labels[i] = idx where d2 < thr_H^2, other labels untouched."""
+    import torch
+
+    d_pts, _ = dev
+    for idx, h in ((0, scene.planes[3]), (7, scene.planes[11])):
+        lab0 = np.full(len(scene.pts), -1, dtype=np.int32); lab0[::5] = 3
+        lab_o = orc.inliers_of_homography(scene.pts, h, 2.2, idx, lab0.copy())
+        d_lab = torch.from_numpy(lab0.copy()).cuda()
+        gpu_ctx.inliers_of_homography(d_pts, gpu_ctx.hypotheses_from_host(h[None]), idx, d_lab)
+        lab_g = d_lab.cpu().numpy()
+        r = gpu_ctx.residuals(d_pts, gpu_ctx.hypotheses_from_host(h[None])).cpu().numpy()[:, 0]
+        sure = np.abs(r - 2.2 ** 2) > 1e-2            # FP32 evaluation: sites within 1e-2 px^2 of the threshold may flip
+        assert np.array_equal(lab_g[sure], lab_o[sure]) and (lab_g != lab_o).sum() <= (~sure).sum()
+        assert (lab_o == idx).sum() > 100
+
+
+def test_pipeline_single_plane_ends_with_k1(mh, orc):
+    """A one-plane scene: the merging step leaves ONE homography, the loop takes the K == 1 exit (MultiH.cpp:280-285,
+    743-768) — labels are 0 for its inliers and -1 elsewhere (never a stale label of an earlier step), as the oracle pipeline."""
+    from ref_pipeline import oracle_process
+
+    hit = 0
+    for n, orat, noise, seed in ((60, 0.0, 0.2, 3), (60, 0.05, 0.2, 2), (60, 0.0, 0.05, 2), (400, 0.05, 0.5, 1)):
+        sc = mh.scenes.make_scene(n, 1, seed=seed, outlier_ratio=orat, noise_px=noise)
+        ctx = mh.Context()
+        lab, H, K = ctx.process(sc.pts, sc.aff, sc.F)
+        lab_o, H_o, info = oracle_process(sc.pts, sc.aff, sc.F, compatibility_check=True)
+        assert K == len(H_o) and np.array_equal(lab, lab_o) and ctx.iterations == info["iterations"], (seed, K, len(H_o))
+        assert lab.max() < max(K, 1) and lab.min() >= -1
+        if info["k1_exit"]:
+            hit += 1
+            want = orc.inliers_of_homography(sc.pts, H[0], 2.2, 0, np.full(len(sc.pts), -1, dtype=np.int32))
+            assert K == 1 and np.array_equal(lab, want)
+    assert hit >= 3, "the K == 1 exit was not reached"
+
+
+def test_cfg4_sampled_rows_vs_oracle(mh, orc):
+    """BASELINE configs[3], the configuration the headline is quoted on, against the FP64 ORACLE (not only against the repo's own
+    dense kernel): 2048 sampled correspondences x all 8192 hypotheses — data-term argmin and costs vs orc.data_cost_sweep."""
+    import torch
+    import bench
+
+    sc, pick = bench.make_workload()
+    ctx = mh.Context()
+    ctx.set_geometry(sc.F, sc.pts)
+    rows = np.random.default_rng(3).choice(len(sc.pts), 2048, replace=False)
+    d_pts, _ = ctx.upload(sc.pts[rows], sc.aff[rows])
+    p_pts, p_aff = ctx.upload(sc.pts[pick], sc.aff[pick])
+    d_hyp = torch.cat([ctx.hypotheses_from_host(sc.planes), ctx.haf_hypotheses(p_pts, p_aff)]).contiguous()
+    hyps = ctx.hypotheses_to_host(d_hyp)                      # the very hypotheses the kernel sees, in FP64 pixels
+    f = ctx.data_cost_fused(d_pts, d_hyp, kmax=0, want_list=False, out={})
+    best = f["best"].cpu().numpy()
+    cost_o = orc.data_cost_dense(sc.pts[rows], hyps, threads=orc.hardware_threads())
+    lab_g, cost_g = (best & 0xFFFFFFFF).astype(np.int64), (best >> 32).astype(np.int64)
+    min_o = cost_o.min(1)
+    # FP32 (normalised coordinates) vs FP64 (pixels): a cost may differ by 1 (measured 5e-5 of all entries), so the minimum may
+    # differ by 1 and near-ties may swap; a handful of sites sit on ill-conditioned HAF hypotheses of outlier correspondences
+    # (|h_i| >> |h_8|), where the FP32 residual itself is only accurate to a few percent
+    near = np.abs(cost_o[np.arange(len(rows)), lab_g] - min_o) <= 1
+    print(f"\n[parity] cfg4: |min cost gpu - oracle| <= 1 on {(np.abs(cost_g - min_o) <= 1).mean():.5f} of the sites, the GPU's label is "
+          f"an oracle minimiser (+-1) on {near.mean():.5f}")
+    assert (np.abs(cost_g - min_o) <= 1).mean() >= 0.999 and (cost_g == min_o).mean() >= 0.995
+    assert near.mean() >= 0.998   # measured 0.99902: 2 of the 2048 sampled sites
+    assert (lab_g == cost_o.argmin(1)).mean() >= 0.99
+    print(f"[parity] cfg4 2048 x 8192 vs FP64 oracle: min cost exact {(cost_g == min_o).mean():.5f}, argmin equal "
+          f"{(lab_g == cost_o.argmin(1)).mean():.5f}")
+
+
+def test_cfg5_pairs_vs_oracle_pipeline(mh, orc):
+    """BASELINE configs[4]: two of the 5000-correspondence scenes of the batched workload through mh_process vs the oracle
+    pipeline (reference GCO): same clusters, same labels."""
+    from ref_pipeline import oracle_process
+
+    for pair in (0, 3):
+        sc = mh.scenes.make_scene(5000, 3 + (pair % 6), seed=0xB200 + 4 + pair)
+        lab, H, K = mh.Context().process(sc.pts, sc.aff, sc.F)
+        lab_o, H_o, info = oracle_process(sc.pts, sc.aff, sc.F, compatibility_check=True)
+        print(f"\n[parity] cfg5 pair {pair}: K gpu={K} oracle={len(H_o)} agreement={(lab == lab_o).mean():.4f} "
+              f"planes generated={3 + pair % 6} outliers={(lab < 0).mean():.3f}")
+        assert K == len(H_o) and (lab == lab_o).mean() == 1.0
+
+
+def test_compatibility_check_large_cluster(mh, orc):
+    """A cluster too large for the shared-memory sort (> 16384 members) takes compat_trial_big_kernel (radix select on
+    recomputed errors): same medians, removals and rand() consumption as the oracle."""
+    sc = mh.scenes.make_scene(40000, 2, seed=12, outlier_ratio=0.25)
+    lab = sc.gt.astype(np.int32).copy()
+    assert np.bincount(lab[lab >= 0]).max() > 16384 + 3
+    H = sc.planes.copy()
+    ctx = mh.Context()
+    ctx.set_geometry(sc.F, sc.pts)
+    ctx.rng_state = 5
+    l, Hn, med = ctx.compatibility_check(sc.pts, lab, H)
+    l_o, H_o, med_o, rem_o, rng_o = orc.compatibility_check(sc.pts, lab, H, sc.F, thr=2.2, min_inliers=20, rng_state=5)
+    assert ctx.rng_state == rng_o and np.array_equal(l, l_o) and np.array_equal(Hn, H_o)
+    assert np.allclose(med, med_o, rtol=1e-6, atol=1e-9), (med, med_o)
