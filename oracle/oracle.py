@@ -2,7 +2,11 @@
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this.
 Nothing here reads /root/reference at run time; `build()` compiles oracle/_ref from it only when it is present
-(the prebuilt oracle/_ref/libgco_ref.so travels to the GPU box).
+(the prebuilt oracle/_ref/libgco_ref.so and oracle/_ref/libmultih_ref.so travel to the GPU box).
+
+oracle/_ref/libmultih_ref.so is the REFERENCE ITSELF: MultiH.cpp, MeanShiftClustering.h, the refinement callbacks and the
+alpha-expansion compiled unmodified, in place, against a mini OpenCV shim (oracle/cvshim/mini_cv.hpp, oracle/ref_multih_wrapper.cpp).
+The `ref_*` functions below call it; tests/test_oracle.py pins the restatement on them.
 """
 from __future__ import annotations
 
@@ -15,6 +19,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = os.path.join(_HERE, "_build", "libmultih_oracle.so")
 _REF = os.path.join(_HERE, "_ref", "libgco_ref.so")
+_REFMH = os.path.join(_HERE, "_ref", "libmultih_ref.so")
 
 _lib = None
 _ref = None
@@ -28,7 +33,10 @@ def build(force: bool = False) -> None:
     """Compile the restatement (always, if stale) and oracle/_ref (only when the reference tree is mounted)."""
     src = os.path.join(_HERE, "multih_oracle.cpp")
     stale = force or not os.path.exists(_LIB) or os.path.getmtime(_LIB) < os.path.getmtime(src)
-    ref_missing = not os.path.exists(_REF) and os.path.isdir("/root/reference")
+    ref_missing = (not os.path.exists(_REF) or not os.path.exists(_REFMH) or
+                   os.path.getmtime(_REFMH) < max(os.path.getmtime(os.path.join(_HERE, "ref_multih_wrapper.cpp")),
+                                                  os.path.getmtime(os.path.join(_HERE, "cvshim", "mini_cv.hpp")))) \
+        and os.path.isdir("/root/reference")
     if stale or ref_missing:
         subprocess.run(["make", "-C", _HERE, "-s"], check=True)
 
@@ -53,6 +61,75 @@ def ref_lib():
         _ref = C.CDLL(_REF)
         _ref.gco_ref_expansion.restype = C.c_int64
     return _ref
+
+
+_refmh = None
+
+
+def ref_multih_lib():
+    """The reference's hot-path sources compiled in place (oracle/_ref/libmultih_ref.so) — None if never built."""
+    global _refmh
+    if _refmh is None:
+        build()
+        if not os.path.exists(_REFMH):
+            return None
+        _refmh = C.CDLL(_REFMH)
+    return _refmh
+
+
+def ref_process(pts, aff, F, thr_fund=2.6, thr=2.2, locality=0.005, lam=0.5, min_inliers=20, rng_state=1, lm=True):
+    """MultiH::Process() of the reference source (MultiH.cpp:32-98) with F injected in place of its RANSAC, MSVC rand(), the exact
+    31-nearest neighbourhood for FLANN, and its LM solver on (lm=True) or leaving the linear solutions untouched (lm=False).
+    Returns (labels of the kept correspondences, H K x 9, dict(pts, haf, iterations, energy, degenerate))."""
+    pts, pp = _d(pts); aff, pa = _d(aff); F, pf = _d(np.asarray(F).reshape(9))
+    N = len(pts)
+    lab = np.full(N, -9, dtype=np.int32); H = np.zeros((4096, 9)); po = np.zeros((N, 4)); ho = np.zeros((N, 9))
+    K, kept, it, dg, en = C.c_int(0), C.c_int(0), C.c_int(0), C.c_int(0), C.c_double(0)
+    rc = ref_multih_lib().ref_multih_process(pp, pa, pf, N, C.c_double(thr_fund), C.c_double(thr), C.c_double(locality), C.c_double(lam),
+                                              int(min_inliers), C.c_uint(rng_state), int(bool(lm)), lab.ctypes.data_as(c_ip),
+                                              H.ctypes.data_as(c_dp), 4096, C.byref(K), po.ctypes.data_as(c_dp),
+                                              ho.ctypes.data_as(c_dp), C.byref(kept), C.byref(it), C.byref(en), C.byref(dg))
+    if rc:
+        raise RuntimeError("the reference's Process() refused the input (fewer than 8 correspondences)")
+    M = kept.value
+    return lab[:M].copy(), H[: K.value].copy(), dict(pts=po[:M].copy(), haf=ho[:M].copy(), iterations=it.value, energy=en.value,
+                                                      degenerate=bool(dg.value))
+
+
+def ref_haf_hypotheses(pts, aff, F):
+    pts, pp = _d(pts); aff, pa = _d(aff); F, pf = _d(np.asarray(F).reshape(9))
+    H = np.zeros((len(pts), 9))
+    ref_multih_lib().ref_haf_hypotheses(pp, pa, pf, len(pts), H.ctypes.data_as(c_dp))
+    return H
+
+
+def ref_homography_3pt(pts1, pts2, F, refine=False):
+    p1, a = _d(pts1); p2, b = _d(pts2); F, pf = _d(np.asarray(F).reshape(9))
+    H = np.zeros(9)
+    ref_multih_lib().ref_homography_3pt(a, b, len(p1), pf, int(refine), H.ctypes.data_as(c_dp))
+    return H.reshape(3, 3)
+
+
+def ref_haf_nonminimal(pts, aff, F, refine=False):
+    pts, pp = _d(pts); aff, pa = _d(aff); F, pf = _d(np.asarray(F).reshape(9))
+    H = np.zeros(9)
+    ref_multih_lib().ref_haf_nonminimal(pp, pa, len(pts), pf, int(refine), H.ctypes.data_as(c_dp))
+    return H.reshape(3, 3)
+
+
+def ref_data_cost_dense(pts, H, lam=0.5, thr=2.2):
+    pts, pp = _d(pts); H, ph = _d(np.asarray(H).reshape(-1, 9))
+    out = np.zeros((len(pts), len(H) + 1), dtype=np.int32)
+    ref_multih_lib().ref_data_cost_dense(pp, len(pts), ph, len(H), C.c_double(lam), C.c_double(thr), out.ctypes.data_as(c_ip))
+    return out
+
+
+def ref_meanshift(data, bw, rng_state=1):
+    data, pd = _d(data)
+    N, D = data.shape
+    centres = np.zeros((N, D)); assign = np.zeros(N, dtype=np.int32); st = C.c_uint(rng_state)
+    Cn = ref_multih_lib().ref_meanshift(pd, N, D, C.c_double(bw), C.byref(st), centres.ctypes.data_as(c_dp), assign.ctypes.data_as(c_ip))
+    return centres[:Cn].copy(), assign, int(st.value)
 
 
 def _d(a):

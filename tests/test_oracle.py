@@ -193,3 +193,69 @@ def test_meanshift_golden(orc):
         assert tuple(stats) == tuple(g[f"{tag}_stats"]) and rng == int(g[f"{tag}_rng"])
         assert cen.shape == g[f"{tag}_centres"].shape and np.allclose(cen, g[f"{tag}_centres"], rtol=1e-9, atol=1e-9)
         assert np.array_equal(asg, g[f"{tag}_assign"])
+
+
+# ---- the oracle against the REFERENCE SOURCE compiled in place (oracle/_ref/libmultih_ref.so) ---------------------------------------
+@pytest.fixture(scope="module")
+def refmh(orc):
+    if orc.ref_multih_lib() is None:
+        pytest.skip("oracle/_ref/libmultih_ref.so was never built (needs /root/reference once)")
+    return orc
+
+
+def test_oracle_functions_equal_reference_source(refmh, scene):
+    """GetHomographyHAF, dataEnergy / smoothnessEnergy, MeanShiftClustering<double>::Cluster, GetHomography3PT and
+    GetHomographyHAFNonminimal of the reference's own MultiH.cpp (compiled unmodified against the mini OpenCV shim) against the
+    oracle's restatement: identical integer costs, identical mean-shift (centres, assignments, rand() consumption), homographies
+    to 1e-7 (two different Jacobi eigen-solvers / SVDs)."""
+    orc = refmh
+    pts, aff, F = scene.pts[:3000], scene.aff[:3000], scene.F
+    Ho, Hr = orc.haf_hypotheses(pts, aff, F), orc.ref_haf_hypotheses(pts, aff, F)
+    rel = np.abs(Hr / Hr[:, 8:9] - Ho / Ho[:, 8:9]).max(1) / np.abs(Ho / Ho[:, 8:9]).max(1)
+    assert np.percentile(rel, 99) < 1e-7 and rel.max() < 1e-5, np.percentile(rel, [50, 99, 100])
+    hyps = np.concatenate([scene.planes, Ho[:50]])
+    assert np.array_equal(orc.ref_data_cost_dense(pts, hyps), orc.data_cost_dense(pts, hyps))
+    assert np.array_equal(orc.ref_data_cost_dense(pts[:200], hyps, lam=0.3, thr=3.1), orc.data_cost_dense(pts[:200], hyps, 0.3, 3.1))
+    assert orc.ref_multih_lib().ref_smooth_cost(0, 1, __import__("ctypes").c_double(0.5)) == orc.smooth_cost(0, 1) == 50
+    f10 = orc.features10(Ho, pts, 0.005)
+    for data, seed in ((f10, 1), (orc.features6(Ho[:400]), 1234)):
+        cr, ar, rr = orc.ref_meanshift(data, 2.2, seed)
+        co, ao, ro, _ = orc.meanshift(data, 2.2, 0, seed)
+        assert rr == ro and cr.shape == co.shape and np.array_equal(ar, ao)
+        assert np.abs(cr - co).max() <= 1e-9
+    for label in range(3):
+        idx = np.where(scene.gt[:3000] == label)[0][:40]
+        H3r, H3o = orc.ref_homography_3pt(pts[idx, :2], pts[idx, 2:], F), orc.homography_3pt(pts[idx, :2], pts[idx, 2:], F)
+        assert np.abs(H3r / H3r[2, 2] - H3o / H3o[2, 2]).max() < 1e-8
+        lab = np.full(len(pts), -1, dtype=np.int32); lab[idx] = 0
+        Hn = orc.ref_haf_nonminimal(pts[idx], aff[idx], F)
+        Hno = orc.refit_haf(pts, aff, lab, 1, F)[0][0].reshape(3, 3)
+        assert np.abs(Hn / Hn[2, 2] - Hno / Hno[2, 2]).max() < 1e-7
+        # RefineHomographyHAF rebinds its local H (Homography_RefineHAFCallback.h:58) and never writes _H: the LM result is dropped
+        Hn_lm = orc.ref_haf_nonminimal(pts[idx], aff[idx], F, refine=True)
+        assert np.abs(Hn_lm / Hn_lm[2, 2] - Hn / Hn[2, 2]).max() < 1e-9
+
+
+def test_oracle_pipeline_equals_reference_process(refmh):
+    """MultiH::Process() of the reference source on the bundled pair (raw rows that pass the F test; F injected) against the
+    oracle pipeline with the refinement filter and the compatibility check: same survivors, clusters, iterations, energy, labels."""
+    import sys
+    sys.path.insert(0, os.path.dirname(__file__))
+    from ref_pipeline import oracle_process
+
+    orc = refmh
+    g = np.load(os.path.join(GOLD, "golden_prefilter.npz"))
+    F = g["barr_F"]
+    x1 = np.c_[g["barr_pts"][:, :2], np.ones(len(g["barr_pts"]))]; x2 = np.c_[g["barr_pts"][:, 2:], np.ones(len(x1))]
+    l = x1 @ F.T
+    inl = np.abs(np.einsum("ij,ij->i", x2, l)) / np.hypot(l[:, 0], l[:, 1]) < 2.6
+    pts, aff = g["barr_pts"][inl], g["barr_aff"][inl]
+    lab_r, H_r, info_r = orc.ref_process(pts, aff, F, lm=False)
+    lab_o, H_o, info_o = oracle_process(pts, aff, F, prefilter=True, compatibility_check=True)
+    keep = lab_o > -2
+    assert keep.sum() == len(lab_r) and not info_r["degenerate"]
+    kp, _, _ = orc.prefilter(pts, aff, F)
+    assert np.abs(kp - info_r["pts"]).max() < 1e-6                                   # the refined coordinates
+    assert len(H_r) == len(H_o) and info_r["iterations"] == info_o["iterations"] and info_r["energy"] == info_o["energy"]
+    assert np.array_equal(lab_r, lab_o[keep])
+    assert np.abs(H_r / H_r[:, 8:9] - H_o / H_o[:, 8:9]).max() < 1e-6
