@@ -131,7 +131,7 @@ def run_reference(args):
 
         g = np.load(os.path.join(ROOT, "tests", "golden", "barrsmith_hotpath_input.npz"))
         tr = time.perf_counter()
-        rlab, rH, rinfo = oracle_process(g["pts"], g["aff"], g["F"])
+        rlab, rH, rinfo = oracle_process(g["pts"], g["aff"], g["F"], compatibility_check=True, lm=True)
         line["pair_e2e"] = {"workload": "bundled barrsmith pair, hot-path input fixture (1197 correspondences)",
                             "ms_per_pair": (time.perf_counter() - tr) * 1e3, "planes": int(len(rH)),
                             "iterations": int(rinfo["iterations"]),
@@ -436,7 +436,7 @@ def main():
                 from ref_pipeline import oracle_process
 
                 tr = time.perf_counter()
-                rlab, rH, rinfo = oracle_process(g["pts"], g["aff"], g["F"])
+                rlab, rH, rinfo = oracle_process(g["pts"], g["aff"], g["F"], compatibility_check=True, lm=True)
                 pair["cpu_reference"] = {"ms_per_pair": (time.perf_counter() - tr) * 1e3, "planes": int(len(rH)),
                                          "iterations": int(rinfo["iterations"]),
                                          "kind": "oracle pipeline (FP64 port) + reference GCO alpha-expansion, 1 run",

@@ -70,6 +70,9 @@ typedef struct mh_params {
                                correspondences get label -2.  0 (default) = inputs are already refined             */
   int32_t compatibility_check; /* mh_process: 1 (default) = finish with HomographyCompatibilityCheck (MultiH.cpp:78-86, 100-222)
                                   as Process() does; 0 = return the clusters of the alternating optimisation              */
+  int32_t lm_refine;           /* 1 (default) = every GetHomography3PT fit that the reference polishes (cluster fits MultiH.cpp:684,
+                                  mode fits :427) goes through its Levenberg-Marquardt iteration (Homography_Refine3PTCallback.h,
+                                  Utilities.hpp:762-869), reproduced step for step; 0 = the linear solutions                */
 } mh_params;
 
 /* main.cpp:55-59: 2.6 / 2.2 / 0.005 / 0.5 / 20 (the CLI's values; the class defaults of MultiH.h:7-10 are what the MultiH
@@ -77,8 +80,9 @@ typedef struct mh_params {
  * MultiH::Process(), all in one place:
  *   - F is an input; the RANSAC of MultiH.cpp:775 and its inlier mask are upstream;
  *   - prefilter = 0 by default (inputs already refined); the shims set 1, as Process() refines every correspondence;
- *   - every fit returns the reference's own linear solution (do_numerical_refinement = false): the LM polish reads out of
- *     bounds (Homography_RefineHAFCallback.h:148-151), see mh_params.lm_refine of a later revision;
+ *   - the LM polish of the 3PT fits is reproduced (lm_refine); the HAF polish (RefineHomographyHAF) is not run: it never writes
+ *     its result back (Homography_RefineHAFCallback.h:58 rebinds a local header), so skipping it changes nothing — and its
+ *     callback reads out of bounds (:148-151);
  *   - the neighbourhood is the exact 31 nearest within the radius (max_neighbours), FLANN's is a randomised 32-check search;
  *   - K <= 1 after the loop: the reference discards everything and calls cv::findHomography (HandleDegenerateCase,
  *     MultiH.cpp:88-94, 719-741); mh_process returns the single surviving homography with its inliers (labels 0 / -1,

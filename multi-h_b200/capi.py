@@ -44,7 +44,7 @@ class Params(C.Structure):
         ("lambda_", C.c_double), ("min_inliers", C.c_int32), ("straightness", C.c_double),
         ("max_iterations", C.c_int32), ("convergence", C.c_double), ("meanshift_metric", C.c_int32),
         ("rng_seed", C.c_uint32), ("max_gc_cycles", C.c_int32), ("max_neighbours", C.c_int32), ("precise_pipeline", C.c_int32), ("prefilter", C.c_int32),
-        ("compatibility_check", C.c_int32),
+        ("compatibility_check", C.c_int32), ("lm_refine", C.c_int32),
     ]
 
 

@@ -153,6 +153,7 @@ void mh_default_params(mh_params* p) {
   p->max_neighbours = 31;    // FLANN default SearchParams: checks = 32 (query included)
   p->precise_pipeline = 1;
   p->prefilter = 0;            // inputs are taken as already refined; the MultiH class shims switch it on (Process() takes raw rows)
+  p->lm_refine = 1;            // the 3PT fits are LM-polished as in the reference (MultiH.cpp:1052-1053)
   p->compatibility_check = 1;  // Process() always ends with HomographyCompatibilityCheck when K > 1 (MultiH.cpp:76-86)
 }
 

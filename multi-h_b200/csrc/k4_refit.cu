@@ -394,12 +394,125 @@ __device__ __forceinline__ void rows_3pt(double x1, double y1, double x2, double
   r[0] += a0 * ra + b0 * rb; r[1] += a1 * ra + b1 * rb; r[2] += a2 * ra + b2 * rb;
 }
 
+// ---- the reference's LM polish of a 3PT fit ----------------------------------------------------------------------------------
+// RefineHomography3PT + Homography_Refine3PTCallback::compute (Homography_Refine3PTCallback.h:7-58, 81-143) driven by the
+// reference's copy of cv::LMSolverImpl::run (Utilities.hpp:762-869; 1000 iterations, epsx = epsf = FLT_EPSILON), step for step:
+// parameters (h31, h32, h33) of H in normalised coordinates, residuals (x2 - x', y2 - y'), the callback's own approximate
+// Jacobian rows e_x s (x1, y1, 1) and e_y s (x1, y1, 1) — they ignore the derivative of the projective division and carry the
+// opposite sign of d(err)/dh, so most trial steps are rejected; whatever the iteration accepts is what the reference keeps, and
+// so does this.  (The HAF polish, RefineHomographyHAF, rebinds a local header at Homography_RefineHAFCallback.h:58 and never
+// writes its result back — there is nothing to reproduce.)  WARP: the members of a cluster are spread over the lanes and every
+// lane follows the same control flow on the warp-summed statistics; otherwise one thread walks all n points.
+struct Lm3Stats { double S, rmax, A[6], v[3]; };
+template <bool WARP, typename Fetch>
+__device__ __forceinline__ void lm3pt_eval(int n, Fetch fetch, const double (&Fn)[9], double ex, double ey, const double (&h)[3],
+                                           bool jac, int lane, Lm3Stats& o) {
+  o.S = 0; o.rmax = 0;
+#pragma unroll
+  for (int k = 0; k < 6; ++k) o.A[k] = 0;
+  o.v[0] = o.v[1] = o.v[2] = 0;
+  for (int i = WARP ? lane : 0; i < n; i += WARP ? 32 : 1) {
+    double x1, y1, x2, y2;
+    fetch(i, x1, y1, x2, y2);
+    double s = h[0] * x1 + h[1] * y1 + h[2];
+    s = fabs(s) > 2.220446049250313e-16 ? 1. / s : 0;
+    const double h21 = ey * h[0] - Fn[0], h22 = ey * h[1] - Fn[1], h23 = ey * h[2] - Fn[2];
+    const double h11 = ex * h[0] + Fn[3], h12 = ex * h[1] + Fn[4], h13 = ex * h[2] + Fn[5];
+    const double e0 = x2 - (h11 * x1 + h12 * y1 + h13) * s, e1 = y2 - (h21 * x1 + h22 * y1 + h23) * s;
+    o.S += e0 * e0 + e1 * e1;
+    o.rmax = fmax(o.rmax, fmax(fabs(e0), fabs(e1)));
+    if (jac) {   // J^T J and J^T r, row by row as mulTransposed / gemm accumulate them
+      const double j0[3] = {ex * s * x1, ex * s * y1, ex * s}, j1[3] = {ey * s * x1, ey * s * y1, ey * s};
+      o.A[0] += j0[0] * j0[0]; o.A[1] += j0[0] * j0[1]; o.A[2] += j0[0] * j0[2];
+      o.A[3] += j0[1] * j0[1]; o.A[4] += j0[1] * j0[2]; o.A[5] += j0[2] * j0[2];
+      o.v[0] += j0[0] * e0; o.v[1] += j0[1] * e0; o.v[2] += j0[2] * e0;
+      o.A[0] += j1[0] * j1[0]; o.A[1] += j1[0] * j1[1]; o.A[2] += j1[0] * j1[2];
+      o.A[3] += j1[1] * j1[1]; o.A[4] += j1[1] * j1[2]; o.A[5] += j1[2] * j1[2];
+      o.v[0] += j1[0] * e1; o.v[1] += j1[1] * e1; o.v[2] += j1[2] * e1;
+    }
+  }
+  if (WARP) {
+    o.S = warp_sum(o.S);
+#pragma unroll
+    for (int of = 16; of > 0; of >>= 1) o.rmax = fmax(o.rmax, __shfl_xor_sync(0xffffffffu, o.rmax, of));
+    if (jac) {
+#pragma unroll
+      for (int k = 0; k < 6; ++k) o.A[k] = warp_sum(o.A[k]);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) o.v[k] = warp_sum(o.v[k]);
+    }
+  }
+}
+// pseudo-inverse of a symmetric 3x3 through its eigen-decomposition (cv::solve / cv::invert with DECOMP_EIG: eigenvalues
+// <= 2 DBL_EPSILON sum |w| are dropped)
+__device__ __forceinline__ void sym3_pinv(const double (&Au)[6], double (&inv)[3][3]) {
+  double A[3][3] = {{Au[0], Au[1], Au[2]}, {Au[1], Au[3], Au[4]}, {Au[2], Au[4], Au[5]}}, V[3][3];
+  jacobi_sym<3>(A, V);
+  const double thr = 2.0 * 2.220446049250313e-16 * (fabs(A[0][0]) + fabs(A[1][1]) + fabs(A[2][2]));
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) inv[i][j] = 0.0;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    if (!(fabs(A[k][k]) > thr)) continue;
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) inv[i][j] += V[i][k] * V[j][k] / A[k][k];
+  }
+}
+template <bool WARP, typename Fetch>
+__device__ __forceinline__ void lm3pt_refine(int n, Fetch fetch, const double (&Fn)[9], double ex, double ey, double (&x)[3], int lane) {
+  const double eps = 1.1920928955078125e-07, deps = 2.220446049250313e-16, Rlo = 0.25, Rhi = 0.75;
+  Lm3Stats cur, trial;
+  lm3pt_eval<WARP>(n, fetch, Fn, ex, ey, x, true, lane, cur);
+  const double D[3] = {cur.A[0], cur.A[3], cur.A[5]};
+  double lambda = 1, lc = 0.75;
+  for (int iter = 0;;) {
+    const double Ap[6] = {cur.A[0] + lambda * D[0], cur.A[1], cur.A[2], cur.A[3] + lambda * D[1], cur.A[4], cur.A[5] + lambda * D[2]};
+    double inv[3][3], d[3], xd[3];
+    sym3_pinv(Ap, inv);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      d[i] = inv[i][0] * cur.v[0] + inv[i][1] * cur.v[1] + inv[i][2] * cur.v[2];
+      xd[i] = x[i] - d[i];
+    }
+    lm3pt_eval<WARP>(n, fetch, Fn, ex, ey, xd, false, lane, trial);
+    const double Ad[3] = {cur.A[0] * d[0] + cur.A[1] * d[1] + cur.A[2] * d[2], cur.A[1] * d[0] + cur.A[3] * d[1] + cur.A[4] * d[2],
+                          cur.A[2] * d[0] + cur.A[4] * d[1] + cur.A[5] * d[2]};
+    const double dS = d[0] * (2 * cur.v[0] - Ad[0]) + d[1] * (2 * cur.v[1] - Ad[1]) + d[2] * (2 * cur.v[2] - Ad[2]);
+    const double R = (cur.S - trial.S) / (fabs(dS) > deps ? dS : 1);
+    if (R > Rhi) {
+      lambda *= 0.5;
+      if (lambda < lc) lambda = 0;
+    } else if (R < Rlo) {
+      const double t = d[0] * cur.v[0] + d[1] * cur.v[1] + d[2] * cur.v[2];
+      double nu = (trial.S - cur.S) / (fabs(t) > deps ? t : 1) + 2;
+      nu = fmin(fmax(nu, 2.), 10.);
+      if (lambda == 0) {
+        sym3_pinv(cur.A, inv);
+        const double maxval = fmax(deps, fmax(fabs(inv[0][0]), fmax(fabs(inv[1][1]), fabs(inv[2][2]))));
+        lambda = lc = 1. / maxval;
+        nu *= 0.5;
+      }
+      lambda *= nu;
+    }
+    if (trial.S < cur.S) {
+      x[0] = xd[0]; x[1] = xd[1]; x[2] = xd[2];
+      lm3pt_eval<WARP>(n, fetch, Fn, ex, ey, x, true, lane, cur);
+    }
+    ++iter;
+    if (!(iter < 1000 && fmax(fabs(d[0]), fmax(fabs(d[1]), fabs(d[2]))) >= eps && cur.rmax >= eps)) break;
+  }
+}
+
 // one warp per cluster
 __global__ void __launch_bounds__(128) cluster_3pt_kernel(const float4* __restrict__ pts,
                                                           const int32_t* __restrict__ members,
                                                           const int32_t* __restrict__ offsets, int C,
                                                           float* __restrict__ hyp, int32_t* __restrict__ keep, HafGeom g,
-                                                          const double* __restrict__ pts64, double* __restrict__ hyp64) {
+                                                          const double* __restrict__ pts64, double* __restrict__ hyp64, int lm) {
   const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (c >= C) return;
@@ -443,9 +556,18 @@ __global__ void __launch_bounds__(128) cluster_3pt_kernel(const float4* __restri
   for (int k = 0; k < 6; ++k) Nq[k] = warp_sum(Nq[k]);
 #pragma unroll
   for (int k = 0; k < 3; ++k) r[k] = warp_sum(r[k]);
+  double h3[3];
+  pinv_normal3(Nq, r, h3);   // every lane holds the same sums
+  if (lm) {   // MultiH.cpp:1052-1053
+    auto fetch = [&](int i, double& x1, double& y1, double& x2, double& y2) {
+      double px1, py1, px2, py2;
+      load_point_px(pts, pts64, members[beg + i], g, px1, py1, px2, py2);
+      x1 = (px1 - nm.mx1) * nm.s1; y1 = (py1 - nm.my1) * nm.s1;
+      x2 = (px2 - nm.mx2) * nm.s2; y2 = (py2 - nm.my2) * nm.s2;
+    };
+    lm3pt_refine<true>(n, fetch, Fn, ex, ey, h3, lane);
+  }
   if (lane == 0) {
-    double h3[3];
-    pinv_normal3(Nq, r, h3);
     assemble_3pt_and_store(h3, Fn, ex, ey, nm, g, hyp + 12 * (size_t)c, hyp64 ? hyp64 + 9 * (size_t)c : nullptr);
     keep[c] = 1;
   }
@@ -459,14 +581,14 @@ mh_status launch_refit_3pt(mh_ctx* ctx, const float4* d_pts, const int32_t* d_as
   MH_TRY(build_csr(ctx, d_assign, N, C, c));
   const unsigned blocks = (unsigned)(((uint64_t)C * 32 + 127) / 128);
   cluster_3pt_kernel<<<blocks, 128, 0, ctx->stream>>>(d_pts, c.members, c.offsets, C, d_hyp, d_keep, haf_geom(ctx), d_pts64,
-                                                      d_hyp64);
+                                                      d_hyp64, ctx->params.lm_refine);
   MH_LAUNCHED(ctx, "cluster_3pt_kernel");
   return MH_OK;
 }
 
 // MergingStep: mode (6-D feature, pixel units) -> homography by 3PT on (0,0),(1,0),(0,1) (MultiH.cpp:408-427).
 __global__ void modes_to_hyp_kernel(const double* __restrict__ modes, int C, float* __restrict__ hyp, HafGeom g,
-                                    double* __restrict__ hyp64) {
+                                    double* __restrict__ hyp64, int lm) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   const double* m = modes + 6 * (size_t)c;
@@ -493,12 +615,19 @@ __global__ void modes_to_hyp_kernel(const double* __restrict__ modes, int C, flo
              (p2[i][1] - nm.my2) * nm.s2, ex, ey, Fn, Nq, r);
   double h3[3];
   pinv_normal3(Nq, r, h3);
+  if (lm) {   // MultiH.cpp:427 calls GetHomography3PT with its default do_numerical_refinement = true
+    auto fetch = [&](int i, double& x1, double& y1, double& x2, double& y2) {
+      x1 = (p1[i][0] - nm.mx1) * nm.s1; y1 = (p1[i][1] - nm.my1) * nm.s1;
+      x2 = (p2[i][0] - nm.mx2) * nm.s2; y2 = (p2[i][1] - nm.my2) * nm.s2;
+    };
+    lm3pt_refine<false>(3, fetch, Fn, ex, ey, h3, 0);
+  }
   assemble_3pt_and_store(h3, Fn, ex, ey, nm, g, hyp + 12 * (size_t)c, hyp64 ? hyp64 + 9 * (size_t)c : nullptr);
 }
 
 mh_status launch_modes_to_hyp(mh_ctx* ctx, const double* d_modes, int C, float* d_hyp, double* d_hyp64) {
   if (C <= 0) return MH_OK;
-  modes_to_hyp_kernel<<<(unsigned)((C + 63) / 64), 64, 0, ctx->stream>>>(d_modes, C, d_hyp, haf_geom(ctx), d_hyp64);
+  modes_to_hyp_kernel<<<(unsigned)((C + 63) / 64), 64, 0, ctx->stream>>>(d_modes, C, d_hyp, haf_geom(ctx), d_hyp64, ctx->params.lm_refine);
   MH_LAUNCHED(ctx, "modes_to_hyp_kernel");
   return MH_OK;
 }

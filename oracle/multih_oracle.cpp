@@ -406,11 +406,125 @@ int orc_meanshift(const double* data, int N, int D, double bw, int metric, uint3
 void orc_normalize_points(const double* pts, int n, double* out, double* T) { normalize_points(pts, n, out, T); }
 
 // ---------------------------------------------------------------------------
-// K4 (3PT) oracle.  MultiH::GetHomography3PT (MH.cpp:995-1055) with
-// do_numerical_refinement=false (the LM callback is not a parity target, see
-// SURVEY.md §8a row 8).  pts1/pts2: n x 2.  Out H (3x3, NOT divided by h33).
+// The reference's Levenberg-Marquardt polish of the 3PT fit: RefineHomography3PT + Homography_Refine3PTCallback
+// (3PTcb.h:7-58, 81-143) driven by its copy of cv::LMSolverImpl::run (Utilities.hpp:762-869, 1000 iterations, eps = FLT_EPSILON),
+// restated step for step.  Parameters: the third row (h31, h32, h33) of H in NORMALISED coordinates; residuals: the reprojection
+// errors (x2 - x', y2 - y'); the callback's Jacobian is the reference's own approximation (e_x s x1, e_x s y1, e_x s; e_y ...) — it
+// ignores the derivative of the projective division and has the opposite sign of d(err)/dh, so most steps are rejected; whatever
+// the iteration accepts is what the reference keeps.  (The HAF polish, RefineHomographyHAF, never writes its result back:
+// HAFcb.h:58 rebinds a local header — its effect is nil, so there is nothing to restate.)
 // ---------------------------------------------------------------------------
+namespace {
+struct Lm3ptProblem { const double *p1, *p2; int n; const double* F; double ex, ey; };
+
+// Homography_Refine3PTCallback::compute (3PTcb.h:81-143): err [2n], J [2n][3] (row-major) when wanted
+void lm3pt_compute(const Lm3ptProblem& P, const double* h, double* err, double* J) {
+  for (int i = 0; i < P.n; ++i) {
+    const double x1 = P.p1[2 * i], y1 = P.p1[2 * i + 1], x2 = P.p2[2 * i], y2 = P.p2[2 * i + 1];
+    double s = h[0] * x1 + h[1] * y1 + h[2];
+    s = std::fabs(s) > DBL_EPSILON ? 1. / s : 0;
+    const double h21 = P.ey * h[0] - P.F[0], h22 = P.ey * h[1] - P.F[1], h23 = P.ey * h[2] - P.F[2];
+    const double h11 = P.ex * h[0] + P.F[3], h12 = P.ex * h[1] + P.F[4], h13 = P.ex * h[2] + P.F[5];
+    const double xi = (h11 * x1 + h12 * y1 + h13) * s, yi = (h21 * x1 + h22 * y1 + h23) * s;
+    err[2 * i] = x2 - xi;
+    err[2 * i + 1] = y2 - yi;
+    if (J) {
+      double* j = J + 6 * (size_t)i;
+      j[0] = P.ex * s * x1; j[1] = P.ex * s * y1; j[2] = P.ex * s;
+      j[3] = P.ey * s * x1; j[4] = P.ey * s * y1; j[5] = P.ey * s;
+    }
+  }
+}
+// x = A^+ b for a symmetric 3x3 A through its eigen-decomposition, as cv::solve / cv::invert do with DECOMP_EIG (back substitution
+// drops eigenvalues <= 2 DBL_EPSILON sum |w|); Ainv optionally returns the pseudo-inverse
+void sym3_eig_solve(const double* A, const double* b, double* x, double* Ainv) {
+  double w[3], V[9];
+  sym_eigen(3, A, w, V);   // eigenvectors in rows
+  double sum = 0;
+  for (int k = 0; k < 3; ++k) sum += std::fabs(w[k]);
+  const double thr = 2 * DBL_EPSILON * sum;
+  double inv[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  for (int k = 0; k < 3; ++k) {
+    if (!(std::fabs(w[k]) > thr)) continue;
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) inv[i * 3 + j] += V[k * 3 + i] * V[k * 3 + j] / w[k];
+  }
+  if (x)
+    for (int i = 0; i < 3; ++i) x[i] = inv[i * 3] * b[0] + inv[i * 3 + 1] * b[1] + inv[i * 3 + 2] * b[2];
+  if (Ainv) std::memcpy(Ainv, inv, sizeof(inv));
+}
+// cv::LMSolverImpl::run (Utilities.hpp:762-869) on the three parameters; returns the iteration count
+int lm3pt_run(const Lm3ptProblem& P, double* x, int maxIters = 1000) {
+  const int m = 2 * P.n;
+  std::vector<double> r(m), rd(m), J(3 * (size_t)m);
+  auto normal = [&](double* A, double* v) {   // A = J^T J, v = J^T r
+    for (int k = 0; k < 9; ++k) A[k] = 0;
+    v[0] = v[1] = v[2] = 0;
+    for (int i = 0; i < m; ++i) {
+      const double* j = J.data() + 3 * (size_t)i;
+      for (int a = 0; a < 3; ++a) {
+        v[a] += j[a] * r[i];
+        for (int b = 0; b < 3; ++b) A[a * 3 + b] += j[a] * j[b];
+      }
+    }
+  };
+  auto sumsq = [&](const std::vector<double>& e) { double s = 0; for (double t : e) s += t * t; return s; };
+  auto maxabs = [](const double* e, int n) { double s = 0; for (int i = 0; i < n; ++i) s = std::max(s, std::fabs(e[i])); return s; };
+  lm3pt_compute(P, x, r.data(), J.data());
+  double S = sumsq(r), A[9], v[3], D[3], Ap[9], d[3], xd[3];
+  normal(A, v);
+  for (int i = 0; i < 3; ++i) D[i] = A[i * 3 + i];
+  const double Rlo = 0.25, Rhi = 0.75, eps = FLT_EPSILON;
+  double lambda = 1, lc = 0.75;
+  int iter = 0;
+  for (;;) {
+    std::memcpy(Ap, A, sizeof(Ap));
+    for (int i = 0; i < 3; ++i) Ap[i * 3 + i] += lambda * D[i];
+    sym3_eig_solve(Ap, v, d, nullptr);
+    for (int i = 0; i < 3; ++i) xd[i] = x[i] - d[i];
+    lm3pt_compute(P, xd, rd.data(), nullptr);
+    const double Sd = sumsq(rd);
+    double dS = 0;   // d . (2 v - A d)
+    for (int i = 0; i < 3; ++i) dS += d[i] * (2 * v[i] - (A[i * 3] * d[0] + A[i * 3 + 1] * d[1] + A[i * 3 + 2] * d[2]));
+    const double R = (S - Sd) / (std::fabs(dS) > DBL_EPSILON ? dS : 1);
+    if (R > Rhi) {
+      lambda *= 0.5;
+      if (lambda < lc) lambda = 0;
+    } else if (R < Rlo) {
+      const double t = d[0] * v[0] + d[1] * v[1] + d[2] * v[2];
+      double nu = (Sd - S) / (std::fabs(t) > DBL_EPSILON ? t : 1) + 2;
+      nu = std::min(std::max(nu, 2.), 10.);
+      if (lambda == 0) {
+        sym3_eig_solve(A, nullptr, nullptr, Ap);
+        double maxval = DBL_EPSILON;
+        for (int i = 0; i < 3; ++i) maxval = std::max(maxval, std::fabs(Ap[i * 3 + i]));
+        lambda = lc = 1. / maxval;
+        nu *= 0.5;
+      }
+      lambda *= nu;
+    }
+    if (Sd < S) {
+      S = Sd;
+      std::memcpy(x, xd, sizeof(xd));
+      lm3pt_compute(P, x, r.data(), J.data());
+      normal(A, v);
+    }
+    ++iter;
+    if (!(iter < maxIters && maxabs(d, 3) >= eps && maxabs(r.data(), m) >= eps)) break;
+  }
+  return iter;
+}
+}  // namespace
+
+// ---------------------------------------------------------------------------
+// K4 (3PT) oracle.  MultiH::GetHomography3PT (MH.cpp:995-1055); refine = its do_numerical_refinement (the LM polish
+// above).  pts1/pts2: n x 2.  Out H (3x3, NOT divided by h33).
+// ---------------------------------------------------------------------------
+void orc_homography_3pt_ex(const double* pts1, const double* pts2, int n, const double* F, int refine, double* H);
 void orc_homography_3pt(const double* pts1, const double* pts2, int n, const double* F, double* H) {
+  orc_homography_3pt_ex(pts1, pts2, n, F, 0, H);
+}
+void orc_homography_3pt_ex(const double* pts1, const double* pts2, int n, const double* F, int refine, double* H) {
   std::vector<double> n1(2 * n), n2(2 * n);
   double T1[9], T2[9], T1i[9], T2i[9];
   normalize_points(pts1, n, n1.data(), T1);
@@ -435,6 +549,10 @@ void orc_homography_3pt(const double* pts1, const double* pts2, int n, const dou
   }
   double h3[3];
   pinv3_solve(A, b, 2 * n, h3);  // MH.cpp:1038
+  if (refine) {  // MH.cpp:1052-1053
+    const Lm3ptProblem P{n1.data(), n2.data(), n, Fn, e[0], e[1]};
+    lm3pt_run(P, h3);
+  }
   double Hn[9];
   const double v[4] = {h3[0], h3[1], h3[2], 1.0};  // lambda == 1 (MH.cpp:1045-1050)
   haf_assemble(v, Fn, e[0], e[1], Hn);
@@ -445,8 +563,14 @@ void orc_homography_3pt(const double* pts1, const double* pts2, int n, const dou
 // Batched form used by EstablishStablePointSets (MH.cpp:664-688): one 3PT fit
 // per cluster over the members listed in CSR (offsets[C+1], members[]).
 // Clusters with < 3 members get keep[c]=0 (MH.cpp:667).
+void orc_cluster_3pt_ex(const double* pts, const int* offsets, const int* members, int C, const double* F, int refine, double* H,
+                        int* keep);
 void orc_cluster_3pt(const double* pts, const int* offsets, const int* members, int C, const double* F, double* H,
                      int* keep) {
+  orc_cluster_3pt_ex(pts, offsets, members, C, F, 0, H, keep);
+}
+void orc_cluster_3pt_ex(const double* pts, const int* offsets, const int* members, int C, const double* F, int refine, double* H,
+                        int* keep) {
   for (int c = 0; c < C; ++c) {
     const int n = offsets[c + 1] - offsets[c];
     keep[c] = n >= 3;
@@ -456,16 +580,17 @@ void orc_cluster_3pt(const double* pts, const int* offsets, const int* members, 
       const double* p = pts + 4 * (size_t)members[offsets[c] + j];
       p1[2 * j] = p[0]; p1[2 * j + 1] = p[1]; p2[2 * j] = p[2]; p2[2 * j + 1] = p[3];
     }
-    orc_homography_3pt(p1.data(), p2.data(), n, F, H + 9 * c);
+    orc_homography_3pt_ex(p1.data(), p2.data(), n, F, refine, H + 9 * c);
   }
 }
 
 // MergingStep's mode -> homography (MH.cpp:408-427): 3PT on (0,0),(1,0),(0,1)
 // and the mode's 6-D feature (x1 y1 x2 y2 x3 y3).
-void orc_mode_to_homography(const double* mode6, const double* F, double* H) {
+void orc_mode_to_homography_ex(const double* mode6, const double* F, int refine, double* H) {
   const double p1[6] = {0, 0, 1, 0, 0, 1};
-  orc_homography_3pt(p1, mode6, 3, F, H);
+  orc_homography_3pt_ex(p1, mode6, 3, F, refine, H);
 }
+void orc_mode_to_homography(const double* mode6, const double* F, double* H) { orc_mode_to_homography_ex(mode6, F, 0, H); }
 
 // ---------------------------------------------------------------------------
 // Post-processing oracle.  MultiH::HomographyCompatibilityCheck (MH.cpp:100-222): a cross-validation filter on the

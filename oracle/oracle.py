@@ -218,16 +218,17 @@ def normalize_points(pts):
     return out, T
 
 
-def homography_3pt(pts1, pts2, F):
+def homography_3pt(pts1, pts2, F, refine=False):
+    """GetHomography3PT (MultiH.cpp:995-1055); refine = do_numerical_refinement (the reference's LM polish, 3PTcb.h)."""
     pts1, p1 = _d(pts1)
     pts2, p2 = _d(pts2)
     F, pF = _d(F)
     H = np.empty((3, 3))
-    lib().orc_homography_3pt(p1, p2, pts1.shape[0], pF, H.ctypes.data_as(c_dp))
+    lib().orc_homography_3pt_ex(p1, p2, pts1.shape[0], pF, int(refine), H.ctypes.data_as(c_dp))
     return H
 
 
-def cluster_3pt(pts, offsets, members, F):
+def cluster_3pt(pts, offsets, members, F, refine=False):
     pts, pp = _d(pts)
     offsets, po = _i32(offsets)
     members, pm = _i32(members)
@@ -235,7 +236,7 @@ def cluster_3pt(pts, offsets, members, F):
     Cn = offsets.shape[0] - 1
     H = np.zeros((Cn, 9))
     keep = np.zeros(Cn, dtype=np.int32)
-    lib().orc_cluster_3pt(pp, po, pm, Cn, pF, H.ctypes.data_as(c_dp), keep.ctypes.data_as(c_ip))
+    lib().orc_cluster_3pt_ex(pp, po, pm, Cn, pF, int(refine), H.ctypes.data_as(c_dp), keep.ctypes.data_as(c_ip))
     return H, keep.astype(bool)
 
 
@@ -257,11 +258,11 @@ def compatibility_check(pts, labels, H, F, thr=2.2, min_inliers=20, rng_state=1)
     return lab, Hc[:Kn], med[:K], rem[:K].astype(bool), int(st.value)
 
 
-def mode_to_homography(mode6, F):
+def mode_to_homography(mode6, F, refine=False):
     m, pm = _d(mode6)
     F, pF = _d(F)
     H = np.empty((3, 3))
-    lib().orc_mode_to_homography(pm, pF, H.ctypes.data_as(c_dp))
+    lib().orc_mode_to_homography_ex(pm, pF, int(refine), H.ctypes.data_as(c_dp))
     return H
 
 

@@ -17,7 +17,7 @@ def _csr(assign, C):
 
 def oracle_process(pts, aff, F, thr=2.2, locality=0.005, lam=0.5, straightness=0.005, max_iterations=500,
                    convergence=1e-5, max_gc_cycles=1000, rng_state=1, max_neighbours=31, prefilter=False, use_ref_gco=True, expansion=None, trace=None,
-                   compatibility_check=False, min_inliers=20):
+                   compatibility_check=False, min_inliers=20, lm=False):
     if prefilter:                                                            # MultiH.cpp:807-838
         pts, aff, keepmask = orc.prefilter(pts, aff, F)
     N = len(pts)
@@ -26,7 +26,7 @@ def oracle_process(pts, aff, F, thr=2.2, locality=0.005, lam=0.5, straightness=0
     f10 = orc.features10(H_pt, pts, locality)                               # :612-646
     centres, assign, rng_state, _ = orc.meanshift(f10, thr, 0, rng_state)   # :654
     offsets, members = _csr(assign, len(centres))
-    Hc, keep = orc.cluster_3pt(pts, offsets, members, F)                    # :664-688
+    Hc, keep = orc.cluster_3pt(pts, offsets, members, F, refine=lm)         # :664-688 (LM polish: 3PTcb.h, when lm)
     hyp = Hc[keep]
     if trace is not None:
         trace["K0"] = len(hyp)
@@ -43,7 +43,7 @@ def oracle_process(pts, aff, F, thr=2.2, locality=0.005, lam=0.5, straightness=0
         if K > 0:                                                            # MergingStep :352-471
             f6 = orc.features6(hyp)
             modes, _, rng_state, _ = orc.meanshift(f6, thr, 0, rng_state)
-            Hm = np.stack([orc.mode_to_homography(mo, F).ravel() for mo in modes]) if len(modes) else np.zeros((0, 9))
+            Hm = np.stack([orc.mode_to_homography(mo, F, refine=lm).ravel() for mo in modes]) if len(modes) else np.zeros((0, 9))
             _, _, _, keep = orc.inlier_stats(pts, Hm, thr, straightness)
             merged = Hm[keep]
             changed = len(merged) != K

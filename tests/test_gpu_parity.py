@@ -79,8 +79,14 @@ def test_k1_k2_golden_vectors(gpu_ctx, orc):
     assert (diff == 0).mean() >= 0.999 and (diff > 1).sum() <= 1
     d_hr, cnt = gpu_ctx.refit_haf(d_pts, d_aff, __import__("torch").from_numpy(g["labels"]).cuda(), 4)
     assert _rel(gpu_ctx.hypotheses_to_host(d_hr), g["refit_H"]).max() <= 1e-5
+    lin = mh_linear = __import__("multih_b200").Context(__import__("multih_b200").capi.default_params(lm_refine=0))   # the golden fits are linear
+    lin.set_geometry(g["F"], g["pts"])
+    d_m = lin.modes_to_hypotheses(__import__("torch").from_numpy(g["modes"]).cuda())
+    assert _rel(lin.hypotheses_to_host(d_m), g["modes_H"]).max() <= 1e-5
+    # with the reference's LM polish (the default) against the oracle's restatement of it
     d_m = gpu_ctx.modes_to_hypotheses(__import__("torch").from_numpy(g["modes"]).cuda())
-    assert _rel(gpu_ctx.hypotheses_to_host(d_m), g["modes_H"]).max() <= 1e-5
+    Hlm = np.stack([orc.mode_to_homography(mo, g["F"], refine=True).ravel() for mo in g["modes"]])
+    assert _rel(gpu_ctx.hypotheses_to_host(d_m), Hlm).max() <= 1e-5
     sc, lmin, keep = gpu_ctx.inlier_stats(d_pts, gpu_ctx.hypotheses_from_host(g["cost_H"]))
     assert np.array_equal(sc[:, 5].astype(np.int64), g["inl_count"]) and np.array_equal(keep, g["inl_keep"])
 
@@ -295,7 +301,7 @@ def test_k3_meanshift_and_k4_3pt_vs_oracle(mh, orc):
     d_h3, keep = ctx.refit_3pt(d_pts, asg, C)
     order = np.argsort(ao, kind="stable"); order = order[ao[order] >= 0]
     offs = np.concatenate([[0], np.cumsum(np.bincount(ao[ao >= 0], minlength=C))]).astype(np.int32)
-    H3o, keep_o = orc.cluster_3pt(sc.pts, offs, order.astype(np.int32), sc.F)
+    H3o, keep_o = orc.cluster_3pt(sc.pts, offs, order.astype(np.int32), sc.F, refine=True)   # product default: lm_refine = 1
     # the cluster fit is compared on the clusters whose member sets are identical (all of them when agree == 1)
     ag = asg.cpu().numpy()
     same = np.array([np.array_equal(np.where(ag == c)[0], np.where(ao == c)[0]) for c in range(C)])
@@ -404,7 +410,7 @@ def test_compatibility_check_vs_oracle(mh, orc):
 
     g = np.load(os.path.join(GOLD, "barrsmith_hotpath_input.npz"))
     lab, Hh, K = mh.Context(mh.capi.default_params(compatibility_check=1)).process(g["pts"], g["aff"], g["F"])
-    lab_o, H_o, _ = oracle_process(g["pts"], g["aff"], g["F"], compatibility_check=True)
+    lab_o, H_o, _ = oracle_process(g["pts"], g["aff"], g["F"], compatibility_check=True, lm=True)
     print(f"\n[parity] barrsmith with compatibility check: K gpu={K} oracle={len(H_o)} agreement={(lab == lab_o).mean():.4f}")
     assert K == len(H_o) and (lab == lab_o).mean() == 1.0
 
@@ -463,7 +469,7 @@ def test_pipeline_labels_vs_oracle(mh, orc):
     params = mh.capi.default_params(locality=1 / 20.0)
     ctx = mh.Context(params)
     lab, H, K = ctx.process(sc.pts, sc.aff, sc.F)
-    lab_o, H_o, info = oracle_process(sc.pts, sc.aff, sc.F, locality=1 / 20.0, compatibility_check=True)
+    lab_o, H_o, info = oracle_process(sc.pts, sc.aff, sc.F, locality=1 / 20.0, compatibility_check=True, lm=True)
     agree, ari = (lab == lab_o).mean(), _ari(lab, lab_o)
     print(f"\n[parity] synthetic 3000x6: K gpu={K} oracle={len(H_o)} label agreement={agree:.4f} ARI={ari:.4f} "
           f"iterations gpu={ctx.iterations} oracle={info['iterations']} outliers gpu={(lab < 0).mean():.3f} "
@@ -484,7 +490,7 @@ def test_pipeline_bundled_pair(mh, orc):
     g = np.load(os.path.join(GOLD, "barrsmith_hotpath_input.npz"))
     ctx = mh.Context()
     lab, H, K = ctx.process(g["pts"], g["aff"], g["F"])
-    lab_o, H_o, info = oracle_process(g["pts"], g["aff"], g["F"], compatibility_check=True)
+    lab_o, H_o, info = oracle_process(g["pts"], g["aff"], g["F"], compatibility_check=True, lm=True)
     agree, ari = (lab == lab_o).mean(), _ari(lab, lab_o)
     big = np.bincount(lab[lab >= 0]).max() / len(lab)
     print(f"\n[parity] barrsmith N={len(lab)}: K gpu={K} oracle={len(H_o)} label agreement={agree:.4f} ARI={ari:.4f} "
@@ -618,7 +624,7 @@ def test_pipeline_from_raw_correspondences(mh, orc):
     pts, aff = g["barr_pts"][inl], g["barr_aff"][inl]
     ctx = mh.Context(mh.capi.default_params(prefilter=1))
     lab, H, K = ctx.process(pts, aff, F)
-    lab_o, H_o, info = oracle_process(pts, aff, F, prefilter=True, compatibility_check=True)
+    lab_o, H_o, info = oracle_process(pts, aff, F, prefilter=True, compatibility_check=True, lm=True)
     agree = (lab == lab_o).mean()
     print(f"\n[parity] raw barrsmith N={len(pts)} kept={int((lab > -2).sum())}: K gpu={K} oracle={len(H_o)} agreement={agree:.4f}")
     assert np.array_equal(lab == -2, lab_o == -2)
@@ -661,7 +667,7 @@ def test_pipeline_single_plane_ends_with_k1(mh, orc):
         sc = mh.scenes.make_scene(n, 1, seed=seed, outlier_ratio=orat, noise_px=noise)
         ctx = mh.Context()
         lab, H, K = ctx.process(sc.pts, sc.aff, sc.F)
-        lab_o, H_o, info = oracle_process(sc.pts, sc.aff, sc.F, compatibility_check=True)
+        lab_o, H_o, info = oracle_process(sc.pts, sc.aff, sc.F, compatibility_check=True, lm=True)
         assert K == len(H_o) and np.array_equal(lab, lab_o) and ctx.iterations == info["iterations"], (seed, K, len(H_o))
         assert lab.max() < max(K, 1) and lab.min() >= -1
         if info["k1_exit"]:
@@ -711,7 +717,7 @@ def test_cfg5_pairs_vs_oracle_pipeline(mh, orc):
     for pair in (0, 3):
         sc = mh.scenes.make_scene(5000, 3 + (pair % 6), seed=0xB200 + 4 + pair)
         lab, H, K = mh.Context().process(sc.pts, sc.aff, sc.F)
-        lab_o, H_o, info = oracle_process(sc.pts, sc.aff, sc.F, compatibility_check=True)
+        lab_o, H_o, info = oracle_process(sc.pts, sc.aff, sc.F, compatibility_check=True, lm=True)
         print(f"\n[parity] cfg5 pair {pair}: K gpu={K} oracle={len(H_o)} agreement={(lab == lab_o).mean():.4f} "
               f"planes generated={3 + pair % 6} outliers={(lab < 0).mean():.3f}")
         assert K == len(H_o) and (lab == lab_o).mean() == 1.0
@@ -731,3 +737,27 @@ def test_compatibility_check_large_cluster(mh, orc):
     l_o, H_o, med_o, rem_o, rng_o = orc.compatibility_check(sc.pts, lab, H, sc.F, thr=2.2, min_inliers=20, rng_state=5)
     assert ctx.rng_state == rng_o and np.array_equal(l, l_o) and np.array_equal(Hn, H_o)
     assert np.allclose(med, med_o, rtol=1e-6, atol=1e-9), (med, med_o)
+
+
+def test_pipeline_equals_the_reference_source(mh, orc):
+    """The drop-in statement itself: mh_process (refinement filter, LM-polished 3PT fits, compatibility check — the defaults of
+    the MultiH shims) against MultiH::Process() of the REFERENCE SOURCE compiled in place (oracle/_ref/libmultih_ref.so: F
+    injected for its RANSAC, MSVC rand(), the exact 31-nearest neighbourhood for FLANN) on the bundled pair and a synthetic
+    scene: same survivors, same number of planes, same labels, same homographies."""
+    if orc.ref_multih_lib() is None:
+        pytest.skip("oracle/_ref/libmultih_ref.so was never built")
+    g = np.load(os.path.join(GOLD, "golden_prefilter.npz"))
+    F = g["barr_F"]
+    x1 = np.c_[g["barr_pts"][:, :2], np.ones(len(g["barr_pts"]))]; x2 = np.c_[g["barr_pts"][:, 2:], np.ones(len(x1))]
+    l = x1 @ F.T
+    inl = np.abs(np.einsum("ij,ij->i", x2, l)) / np.hypot(l[:, 0], l[:, 1]) < 2.6
+    sc = mh.scenes.make_scene(2500, 4, seed=17)
+    for name, pts, aff, Fm in (("barrsmith", g["barr_pts"][inl], g["barr_aff"][inl], F), ("synthetic 2500x4", sc.pts, sc.aff, sc.F)):
+        lab, H, K = mh.Context(mh.capi.default_params(prefilter=1)).process(pts, aff, Fm)
+        lab_r, H_r, info = orc.ref_process(pts, aff, Fm, lm=True)
+        kept = lab > -2
+        print(f"\n[parity] {name} vs the reference source: kept gpu={int(kept.sum())} ref={len(lab_r)} K gpu={K} ref={len(H_r)} "
+              f"agreement={(lab[kept] == lab_r).mean() if kept.sum() == len(lab_r) else float('nan'):.4f} "
+              f"outliers={(lab_r < 0).mean():.3f} sizes={np.bincount(lab_r[lab_r >= 0]).tolist()}")
+        assert kept.sum() == len(lab_r) and K == len(H_r) and np.array_equal(lab[kept], lab_r)
+        assert np.abs(H / H[:, 8:9] - H_r / H_r[:, 8:9]).max() <= 1e-6

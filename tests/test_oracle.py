@@ -250,12 +250,35 @@ def test_oracle_pipeline_equals_reference_process(refmh):
     l = x1 @ F.T
     inl = np.abs(np.einsum("ij,ij->i", x2, l)) / np.hypot(l[:, 0], l[:, 1]) < 2.6
     pts, aff = g["barr_pts"][inl], g["barr_aff"][inl]
-    lab_r, H_r, info_r = orc.ref_process(pts, aff, F, lm=False)
-    lab_o, H_o, info_o = oracle_process(pts, aff, F, prefilter=True, compatibility_check=True)
-    keep = lab_o > -2
-    assert keep.sum() == len(lab_r) and not info_r["degenerate"]
-    kp, _, _ = orc.prefilter(pts, aff, F)
-    assert np.abs(kp - info_r["pts"]).max() < 1e-6                                   # the refined coordinates
-    assert len(H_r) == len(H_o) and info_r["iterations"] == info_o["iterations"] and info_r["energy"] == info_o["energy"]
-    assert np.array_equal(lab_r, lab_o[keep])
-    assert np.abs(H_r / H_r[:, 8:9] - H_o / H_o[:, 8:9]).max() < 1e-6
+    for lm in (True, False):   # the reference as it is (its LM polish on), and with LM leaving the linear solutions untouched
+        lab_r, H_r, info_r = orc.ref_process(pts, aff, F, lm=lm)
+        lab_o, H_o, info_o = oracle_process(pts, aff, F, prefilter=True, compatibility_check=True, lm=lm)
+        keep = lab_o > -2
+        assert keep.sum() == len(lab_r) and not info_r["degenerate"]
+        kp, _, _ = orc.prefilter(pts, aff, F)
+        assert np.abs(kp - info_r["pts"]).max() < 1e-6                                   # the refined coordinates
+        assert len(H_r) == len(H_o) and info_r["iterations"] == info_o["iterations"] and info_r["energy"] == info_o["energy"]
+        assert np.array_equal(lab_r, lab_o[keep])
+        assert np.abs(H_r / H_r[:, 8:9] - H_o / H_o[:, 8:9]).max() < 1e-6
+
+
+def test_oracle_lm_equals_reference_lm(refmh, mh):
+    """GetHomography3PT with do_numerical_refinement = true: the oracle's restatement of RefineHomography3PT + LMSolverImpl::run
+    against the reference source, on clean clusters, contaminated clusters and three-point mode fits."""
+    orc = refmh
+    sc = mh.scenes.make_scene(3000, 5, seed=3)
+    rng = np.random.default_rng(0)
+    moved = 0
+    for t in range(12):
+        idx = np.where(sc.gt == t % 5)[0][:60] if t < 5 else rng.choice(len(sc.pts), 3 if t >= 9 else 30, replace=False)
+        Hr = orc.ref_homography_3pt(sc.pts[idx, :2], sc.pts[idx, 2:], sc.F, refine=True)
+        Ho = orc.homography_3pt(sc.pts[idx, :2], sc.pts[idx, 2:], sc.F, refine=True)
+        Hl = orc.homography_3pt(sc.pts[idx, :2], sc.pts[idx, 2:], sc.F, refine=False)
+        assert np.abs(Hr / Hr[2, 2] - Ho / Ho[2, 2]).max() < 1e-8
+        moved += np.abs(Ho / Ho[2, 2] - Hl / Hl[2, 2]).max() > 1e-9
+    for mo in orc.features6(sc.planes) + rng.normal(0, 0.7, (5, 6)):   # MergingStep's fits: three synthetic points
+        Hr = orc.ref_homography_3pt(np.array([[0, 0], [1, 0], [0, 1.0]]), mo.reshape(3, 2), sc.F, refine=True)
+        Ho = orc.mode_to_homography(mo, sc.F, refine=True)
+        assert np.abs(Hr / Hr[2, 2] - Ho / Ho[2, 2]).max() < 1e-8
+        moved += np.abs(Ho / Ho[2, 2] - orc.mode_to_homography(mo, sc.F) / orc.mode_to_homography(mo, sc.F)[2, 2]).max() > 1e-9
+    print(f"\n[oracle] LM moved {moved} of 17 fits")
