@@ -93,6 +93,18 @@ void sym_eigen3_host(const double* A, double* w, double* Vrows);
     mh_status _st = mh::check_cuda((ctx), cudaGetLastError(), name);        \
     if (_st != MH_OK) return _st;                                           \
   } while (0)
+// Opt-in for more than 48 KB of dynamic shared memory.  The attribute belongs to the FUNCTION (per device), not to a launch:
+// contexts on several host threads launch the same kernels with different sizes, so it is always set to the hardware maximum —
+// an idempotent call that cannot race with another thread's launch.
+constexpr int MH_MAX_SMEM_PER_BLOCK = 227 * 1024;
+template <typename Kernel>
+inline cudaError_t mh_allow_max_smem(Kernel kernel) {
+  cudaFuncAttributes a;
+  const cudaError_t e = cudaFuncGetAttributes(&a, kernel);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MH_MAX_SMEM_PER_BLOCK - (int)a.sharedSizeBytes);
+}
+
 #define MH_TRY(expr)                                                        \
   do {                                                                      \
     mh_status _st = (expr);                                                 \

@@ -407,7 +407,7 @@ static mh_status launch_tiled(mh_ctx* ctx, const float4* d_pts, int64_t N, const
   if (Kt > 0) {
     const int nchunks = (Kt + DT_KC - 1) / DT_KC;
     auto kern = cost_dense_tiled_kernel<OutT, CONV>;
-    MH_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MH_CUDA(ctx, mh_allow_max_smem(kern));
     int occ = 1;
     MH_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, DT_THREADS, smem));
     const long long resident = (long long)std::max(1, occ) * ctx->sm_count;

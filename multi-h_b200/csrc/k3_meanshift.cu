@@ -862,11 +862,11 @@ template <int DT>
 static mh_status launch_ms_kernels(mh_ctx* ctx, const MsProblem& p, size_t replay_smem, int mode) {
   const int blocks = std::max(1, std::min((p.N + 7) / 8, ctx->sm_count * 8));
   constexpr size_t traj_smem = sizeof(MsWarpScratch) * (MS_TRAJ_THREADS / 32);
-  MH_CUDA(ctx, cudaFuncSetAttribute(ms_trajectories_kernel<DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)traj_smem));
+  MH_CUDA(ctx, mh_allow_max_smem(ms_trajectories_kernel<DT>));
   ms_trajectories_kernel<DT><<<blocks, MS_TRAJ_THREADS, traj_smem, ctx->stream>>>(p);
   MH_LAUNCHED(ctx, "ms_trajectories_kernel");
   auto kern = mode == 0 ? ms_replay_kernel<DT, 0> : mode == 1 ? ms_replay_kernel<DT, 1> : ms_replay_kernel<DT, 2>;
-  MH_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)replay_smem));
+  MH_CUDA(ctx, mh_allow_max_smem(kern));
   kern<<<1, MS_REPLAY_THREADS, replay_smem, ctx->stream>>>(p);
   MH_LAUNCHED(ctx, "ms_replay_kernel");
   return MH_OK;
@@ -952,7 +952,7 @@ mh_status launch_meanshift(mh_ctx* ctx, const double* d_feat, int N, int D, doub
       int P = 32;
       while (P < N) P <<= 1;
       const size_t smem = (size_t)P * 12;
-      MH_CUDA(ctx, cudaFuncSetAttribute(ms_prep_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      MH_CUDA(ctx, mh_allow_max_smem(ms_prep_small_kernel));
       ms_prep_small_kernel<<<1, std::min(1024, std::max(32, P / 2)), smem, ctx->stream>>>(p, P);
       MH_LAUNCHED(ctx, "ms_prep_small_kernel");
     } else {

@@ -883,7 +883,7 @@ mh_status launch_compat_trials(mh_ctx* ctx, const double* d_pts64, const int32_t
   int P = 2;
   while (P < std::min(max_n, COMPAT_SMEM_MAX_N)) P <<= 1;
   const size_t smem = (size_t)P * sizeof(double);
-  MH_CUDA(ctx, cudaFuncSetAttribute(compat_trial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  MH_CUDA(ctx, mh_allow_max_smem(compat_trial_kernel));
   compat_trial_kernel<<<dim3((unsigned)trials, (unsigned)T), COMPAT_THREADS, smem, ctx->stream>>>(
       d_pts64, d_members, d_moff, d_samples, trials, P, haf_geom(ctx), d_out);
   MH_LAUNCHED(ctx, "compat_trial_kernel");
