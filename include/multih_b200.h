@@ -58,7 +58,8 @@ typedef struct mh_params {
   double straightness;    /* DEFAULT_LINENESS_THRESHOLD 0.005 (MultiH.h:13)                    */
   int32_t max_iterations; /* MAX_ITERATION_NUMBER 500 (MultiH.h:14)                            */
   double convergence;     /* CONVERGENCE_THRESHOLD 1e-5 (MultiH.h:15)                          */
-  int32_t meanshift_metric; /* 0 = L1_REF (MeanShiftClustering.h:76-85), 1 = L2                */
+  int32_t meanshift_metric; /* 0 = L1_REF (MeanShiftClustering.h:76-85, the reference), 1 = L2 window, same sequential
+                               algorithm; 2 = L2 window, all seeds batched, Gram on the tensor cores (tcgen05; parity T3) */
   uint32_t rng_seed;      /* state of the injected MSVC-rand() restatement (1 = unseeded rand) */
   int32_t max_gc_cycles;  /* expansion(iter, 1000)  (MultiH.cpp:543)                           */
   int32_t max_neighbours; /* 31: FLANN default checks=32 caps radiusMatch (MultiH.cpp:252-253) at the ~31 nearest

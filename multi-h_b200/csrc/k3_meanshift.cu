@@ -872,6 +872,10 @@ static mh_status launch_ms_kernels(mh_ctx* ctx, const MsProblem& p, size_t repla
   return MH_OK;
 }
 
+uint64_t gram_scratch_bytes(int N, int D);   // k3_gram.cu: the batched L2 member on the tensor cores (metric 2)
+mh_status launch_meanshift_gram(mh_ctx* ctx, const double* d_xs, const int32_t* d_perm, const int32_t* d_nf, int N, int Npad, int D,
+                                double bw, void* scratch, double* d_centres, int max_c, int32_t* d_assign, int* C_out, int64_t* stats);
+
 mh_status launch_meanshift(mh_ctx* ctx, const double* d_feat, int N, int D, double bw, int metric, uint32_t* rng_state,
                            double* d_centres, int max_c, int32_t* d_assign, int* C_out, int64_t* stats) {
   if (D > MS_MAXD) return fail(ctx, MH_EINVAL, "mh_meanshift: D > 16");
@@ -911,6 +915,7 @@ mh_status launch_meanshift(mh_ctx* ctx, const double* d_feat, int N, int D, doub
     const uint64_t o_keys = take(small ? 0 : sizeof(unsigned long long) * 2 * (uint64_t)N);
     const uint64_t o_idx = take(small ? 0 : sizeof(int32_t) * 2 * (uint64_t)N);
     const uint64_t o_cub = take(cub_bytes);
+    const uint64_t o_gram = take(metric == 2 ? gram_scratch_bytes(N, D) : 0);
     MH_TRY(ensure_scratch(ctx, off));
     char* base = (char*)ctx->scratch;
 
@@ -971,6 +976,8 @@ mh_status launch_meanshift(mh_ctx* ctx, const double* d_feat, int N, int D, doub
       ms_gather_kernel<<<(N + 255) / 256, 256, 0, ctx->stream>>>(p, idx + N);
       MH_LAUNCHED(ctx, "ms_gather_kernel");
     }
+    if (metric == 2)   // all seeds at once, L2 window, Gram on the tensor cores: k3_gram.cu
+      return launch_meanshift_gram(ctx, p.xs, p.perm, p.ctl + 2, N, Npad, D, bw, base + o_gram, d_centres, max_c, d_assign, C_out, stats);
     size_t replay_smem = sizeof(MsShared) + sizeof(uint32_t) * (size_t)std::min(mask_words, MS_SMEM_MASK_WORDS);
     const size_t centre_bytes = sizeof(double) * (size_t)D * std::max(max_c, 1);
     const bool centres_smem = mask_words <= MS_SMEM_MASK_WORDS && replay_smem + centre_bytes <= 200 * 1024;

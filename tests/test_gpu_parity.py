@@ -335,6 +335,38 @@ def test_k3_meanshift_l2_metric_vs_oracle(mh, orc):
     assert st != st0   # the two windows really differ on this input
 
 
+def test_k3_meanshift_gram_tensor_core_variant(mh, orc):
+    """meanshift_metric = 2: the batched L2 member whose pairwise-distance Gram runs on the tensor cores (tcgen05 kind::tf32,
+    3xTF32, accumulators in TMEM; csrc/k3_gram.cu).  Every point is a seed, so it is compared with the oracle's sequential L2
+    mean-shift as mode SETS (parity tier T3): every mode the oracle finds has a tensor-core mode within bw/2, the populated
+    clusters (>= 3 members, the ones EstablishStablePointSets keeps) agree in number up to 20 %, and points that the oracle puts
+    into one populated cluster mostly share a cluster here."""
+    import torch
+
+    bw = 2.2
+    for n, seed in ((3000, 7), (9000, 11)):
+        sc = mh.scenes.make_scene(n, 6, seed=seed)
+        fo = orc.features10(orc.haf_hypotheses(sc.pts, sc.aff, sc.F), sc.pts, 0.005)
+        cen, asg, st = mh.Context(mh.capi.default_params(meanshift_metric=2)).meanshift(torch.from_numpy(fo).cuda(), bw)
+        cen, asg = cen.cpu().numpy(), asg.cpu().numpy()
+        co, ao, _, _ = orc.meanshift(fo, bw, metric=1)
+        assert asg.min() >= 0 and asg.max() < len(cen) and st[0] == n
+        d = np.sqrt(((co[:, None, :] - cen[None, :, :]) ** 2).sum(-1))
+        assert (d.min(1) < bw / 2).mean() >= 0.98, (d.min(1) < bw / 2).mean()          # oracle modes are found
+        big_o, big_g = np.bincount(ao[ao >= 0], minlength=len(co)) >= 3, np.bincount(asg, minlength=len(cen)) >= 3
+        assert abs(int(big_g.sum()) - int(big_o.sum())) <= 0.2 * big_o.sum() + 3, (big_g.sum(), big_o.sum())
+        # co-membership: of the oracle's populated clusters, the share of members that land in the tensor-core cluster holding
+        # most of them
+        kept, tot = 0, 0
+        for c in np.where(big_o)[0]:
+            mem = asg[ao == c]
+            kept += np.bincount(mem).max(); tot += len(mem)
+        print(f"\n[parity] K3 tensor-core L2 (N={n}): modes gram={len(cen)} oracle={len(co)}, populated {int(big_g.sum())} vs "
+              f"{int(big_o.sum())}, oracle modes matched {(d.min(1) < bw / 2).mean():.4f}, co-membership {kept / tot:.4f}, "
+              f"iterations {st[1]}")
+        assert kept / tot >= 0.7   # (the oracle assigns by window votes, this member by each point's own trajectory)
+
+
 def test_k3_meanshift_cooperative_path_vs_oracle(mh, orc):
     """N > 8192 takes the persistent cooperative kernel (chip-wide passes, grid barriers); N <= 8192 above takes the one-CTA
     variant.  Same statement for both: the oracle's trajectories, window iterations and centres."""
