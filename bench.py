@@ -257,48 +257,33 @@ def main():
     k2_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
              for _ in range(args.steps + args.warmup + 1)]
 
-    # Multi-GPU: the statistics all-reduce of step i runs on NCCL's stream while step i+1 computes (double-buffered
-    # statistics); its solve is issued when the reduction has landed.  Everything of every step completes inside the
-    # timed region (finish_pending() before the closing event).
-    acc2 = [acc, torch.empty_like(acc)]
-    inl_total = torch.empty_like(fused["inliers"])  # whole-scene inlier counts (after the all-reduce)
-    state = {"cur": 0, "pending": None}
+    # Multi-GPU: the library owns the communicator (mh_comm_init) and the whole sharded pass (mh_step_sharded): hypothesis
+    # broadcast on the communicator's stream under K1, K2, labels, K4 statistics, ONE all-reduce (statistics + inlier counts)
+    # that overlaps the next pass (double-buffered), K4 solves.  torch.distributed only carries the 128-byte id and the
+    # bench's own bookkeeping (barrier, max over ranks).  Everything of every step completes inside the timed region
+    # (finish_pending() before the closing event).
+    if world > 1:
+        ctx.comm_init(rank, world)
+    for pair in k2_ev:          # torch creates the cudaEvent_t lazily: record once so that the handles exist
+        for e in pair:
+            e.record()
 
     def finish_pending():
-        pend = state["pending"]
-        if pend is not None:
-            handle, b = pend
-            handle.wait()
-            ctx.pack_inlier_counts(inl_total, acc2[b], unpack=True)
-            ctx.refit_haf_solve(acc2[b], d_ref)                                              # K4 solves
-            state["pending"] = None
-
-    def stats_and_refit():
-        """K2 outputs -> labels -> K4 statistics; ONE all-reduce carries refit statistics + inlier counts"""
-        b = state["cur"]
-        ctx.labels_from_best(fused["best"], labels)                                          # -1 = outlier
-        d_ref.copy_(d_hyp)
-        ctx.refit_haf_accumulate(d_pts, d_aff, labels, K_HYP, out=acc2[b])                   # K4 statistics
-        if world > 1:
-            ctx.pack_inlier_counts(fused["inliers"], acc2[b])
-            handle = dist.all_reduce(acc2[b], async_op=True)
-            finish_pending()                                                                 # previous step's reduction
-            state["pending"] = (handle, b)
-            state["cur"] = b ^ 1
-        else:
-            ctx.refit_haf_solve(acc2[b], d_ref)                                              # K4 solves
+        ctx.step_sharded_finish()
 
     def hot_pass(ev=None):
-        bc = dist.broadcast(d_hyp, src=0, async_op=True) if world > 1 else None              # overlaps K1
-        ctx.haf_hypotheses(d_pts, d_aff, out=d_hyp_pt)                                      # K1
-        if bc is not None:
-            bc.wait()
-        if ev is not None:
-            ev[0].record()
-        ctx.data_cost_fused(d_pts, d_hyp, kmax=0, want_list=False, out=fused)                # K2
-        if ev is not None:
-            ev[1].record()
-        stats_and_refit()
+        ctx.step_sharded(d_pts, d_aff, d_hyp, d_hyp_pt, fused["best"], labels, fused["inliers"], d_ref, events=ev)
+
+    def stats_and_refit():
+        """e2e ordering (K2 before K1): labels -> K4 statistics -> all-reduce -> solves, in stream order"""
+        ctx.labels_from_best(fused["best"], labels)                                          # -1 = outlier
+        d_ref.copy_(d_hyp)
+        ctx.refit_haf_accumulate(d_pts, d_aff, labels, K_HYP, out=acc)                       # K4 statistics
+        if world > 1:
+            ctx.pack_inlier_counts(fused["inliers"], acc)
+            ctx.comm_allreduce_sum_f64(acc)
+            ctx.pack_inlier_counts(fused["inliers"], acc, unpack=True)
+        ctx.refit_haf_solve(acc, d_ref)                                                      # K4 solves
 
     # end-to-end: the two host->device uploads run on their own stream (second context = second stream, same geometry);
     # K2 needs only the points, so it starts as soon as they have landed and hides the upload of the affines.
@@ -313,13 +298,12 @@ def main():
         ctx_up.upload(h_pts, None, out=(d_pts, None)); ev_pts.record(s_up)                  # H2D + normalise (points)
         ctx_up.upload(None, h_aff, out=(None, d_aff)); ev_aff.record(s_up)                  # H2D + normalise (affines)
         if world > 1:
-            dist.broadcast(d_hyp, src=0)
+            ctx.comm_broadcast(d_hyp, root=0)
         main.wait_event(ev_pts)
         ctx.data_cost_fused(d_pts, d_hyp, kmax=0, want_list=False, out=fused)                # K2
         main.wait_event(ev_aff)
         ctx.haf_hypotheses(d_pts, d_aff, out=d_hyp_pt)                                      # K1
         stats_and_refit()                                                                    # K4 (+ all-reduce)
-        finish_pending()                                                                     # e2e: results of THIS step
         h_labels.copy_(labels, non_blocking=True)                                            # D2H results
         h_ref.copy_(d_ref, non_blocking=True)
         torch.cuda.synchronize()

@@ -43,7 +43,7 @@ typedef enum mh_status {
   MH_OK = 0,
   MH_EINVAL = 1,      /* bad argument (null pointer, N < 8 where the reference refuses: MultiH.cpp:44-50, ...) */
   MH_ECUDA = 2,       /* CUDA runtime / launch failure, or no device */
-  MH_ENCCL = 3,       /* reserved for the multi-GPU layer */
+  MH_ENCCL = 3,       /* NCCL not loadable, or a communicator / collective call failed (mh_comm_*, mh_step_sharded) */
   MH_EDEGENERATE = 4, /* degenerate geometry (||F|| < 1e-5: MultiH.cpp:779; no cluster left) */
   MH_ENOMEM = 5
 } mh_status;
@@ -258,6 +258,35 @@ int32_t mh_get_iterations(const mh_ctx* ctx);   /* GetIterationNumber (MultiH.h:
 /* stage timers mirroring the reference's printf timers (MultiH.cpp:68,74,258,310): ms for
  * [0] point-wise homographies [1] stable clusters [2] adjacency [3] alternating optimisation [4] total */
 mh_status mh_get_stage_ms(const mh_ctx* ctx, double ms[5]);
+
+/* ---- multi-GPU: correspondences sharded over ranks, hypotheses replicated ---------------------------
+ * The reference is one CPU process; its dataEnergy loop (MultiH.cpp:909-924) is independent per correspondence and its
+ * refits (HomographyHAFNonminimal, MultiH.cpp:1057-1115) are sums over members, so the path shards over correspondences
+ * with one broadcast (hypotheses) and one all-reduce (refit statistics + inlier counts) per pass.  One context = one
+ * device = one rank.  NCCL is bound at run time (the libnccl.so.2 already in the process, else dlopen, else $MH_NCCL_LIB);
+ * every failure of that layer is MH_ENCCL with the NCCL message in mh_last_error.
+ *   mh_comm_unique_id    rank 0 makes the 128-byte id; the caller carries it to the other ranks (MPI, file, socket, ...)
+ *   mh_comm_init         collective over `world` contexts; mh_destroy (or mh_comm_destroy) releases the communicator
+ *   mh_comm_broadcast / mh_comm_allreduce_sum_f64   the two collectives on the context's stream (building blocks)
+ *   mh_step_sharded      one whole sharded pass: broadcast of d_hyp f32 [K][12] from rank 0 (on the communicator's own
+ *                        stream, under K1) -> K1 into d_hyp_pt [n_local][12] -> K2 fused into d_best u64 [n_local] ->
+ *                        d_labels i32 [n_local] -> K4 statistics of the shard -> ONE all-reduce (statistics + inlier counts)
+ *                        -> K4 solves into d_ref f32 [K][12], whole-scene counts into d_inliers i32 [K].  The all-reduce
+ *                        of pass i overlaps pass i+1 (double-buffered): d_ref / d_inliers of pass i are complete after
+ *                        the next mh_step_sharded or after mh_step_sharded_finish.  Without a communicator the same call
+ *                        runs the single-GPU pass and completes in stream order.  ev_k2_*: optional cudaEvent_t recorded
+ *                        around the K2 launch. */
+mh_status mh_comm_unique_id(void* id128);
+mh_status mh_comm_init(mh_ctx* ctx, const void* id128, int32_t rank, int32_t world);
+mh_status mh_comm_destroy(mh_ctx* ctx);
+int32_t mh_comm_rank(const mh_ctx* ctx);
+int32_t mh_comm_world(const mh_ctx* ctx);
+mh_status mh_comm_broadcast(mh_ctx* ctx, void* d_buf, uint64_t bytes, int32_t root);
+mh_status mh_comm_allreduce_sum_f64(mh_ctx* ctx, void* d_buf, uint64_t count);
+mh_status mh_step_sharded(mh_ctx* ctx, const void* d_pts, const void* d_aff, int64_t n_local, void* d_hyp, int32_t K,
+                          void* d_hyp_pt, void* d_best, void* d_labels, void* d_inliers, void* d_ref, void* ev_k2_begin,
+                          void* ev_k2_end);
+mh_status mh_step_sharded_finish(mh_ctx* ctx);
 
 /* ---- diagnostics (measurement aids, not part of the reference surface) -------- */
 /* FP32 FMA-pipe peak of this GPU: variant 0 = scalar FFMA, 1 = packed FFMA2; the roofline denominator of K2. */

@@ -28,6 +28,8 @@ SYMBOLS = [
     "mh_inlier_stats", "mh_inliers_of_homography", "mh_features10", "mh_features6", "mh_set_rng_state", "mh_get_rng_state", "mh_meanshift", "mh_refit_haf",
     "mh_refit_haf_accumulate", "mh_refit_haf_solve", "mh_labels_from_best", "mh_pack_inlier_counts", "mh_refit_3pt", "mh_modes_to_hypotheses", "mh_neighbourhood", "mh_alpha_expansion", "mh_compatibility_check", "mh_compat_plan", "mh_compat_decide", "mh_process", "mh_get_energy",
     "mh_get_iterations", "mh_get_stage_ms", "mh_diag_fp32_peak", "mh_diag_mma_tf32_peak", "mh_diag_set_fused_variant", "mh_diag_set_fast_config", "mh_diag_get_fast_config", "mh_diag_set_dense_variant", "mh_diag_get_alternating_ms", "mh_diag_set_neighbourhood_backend",
+    "mh_comm_unique_id", "mh_comm_init", "mh_comm_destroy", "mh_comm_rank", "mh_comm_world", "mh_comm_broadcast",
+    "mh_comm_allreduce_sum_f64", "mh_step_sharded", "mh_step_sharded_finish",
 ]
 
 
@@ -77,7 +79,7 @@ def lib():
         for name in SYMBOLS:
             fn = getattr(L, name)
             if name not in ("mh_last_error", "mh_version", "mh_kernel_launches", "mh_get_energy", "mh_get_iterations",
-                            "mh_get_rng_state",
+                            "mh_get_rng_state", "mh_comm_rank", "mh_comm_world",
                             "mh_default_params", "mh_destroy"):
                 fn.restype = C.c_int
         _lib = L
@@ -369,6 +371,59 @@ class Context:
     def refit_haf_solve(self, d_acc, d_hyp, d_count=None):
         self._check(lib().mh_refit_haf_solve(self._h, _vp(d_acc), int(d_acc.shape[0]), _vp(d_hyp), _vp(d_count)))
         return d_hyp
+
+    # -- multi-GPU (csrc/comm.cu): the library's own NCCL communicator over the ranks that shard the correspondences
+    def comm_init(self, rank: int, world: int, exchange=None):
+        """Collective.  `exchange(id_bytes_or_None) -> id_bytes` carries rank 0's 128-byte NCCL id to every rank; the default
+        uses torch.distributed's object broadcast (any initialised backend — it moves 128 bytes, once)."""
+        ident = None
+        if rank == 0:
+            buf = (C.c_char * 128)()
+            st = lib().mh_comm_unique_id(buf)
+            if st != 0:
+                raise MHError(st, "mh_comm_unique_id: NCCL not loadable (set MH_NCCL_LIB)")
+            ident = bytes(buf.raw)
+        if exchange is None:
+            import torch.distributed as dist
+
+            def exchange(b):
+                box = [b]
+                dist.broadcast_object_list(box, src=0)
+                return box[0]
+        ident = exchange(ident)
+        self._check(lib().mh_comm_init(self._h, C.c_char_p(ident), int(rank), int(world)))
+
+    def comm_destroy(self):
+        self._check(lib().mh_comm_destroy(self._h))
+
+    @property
+    def comm_world(self) -> int:
+        return int(lib().mh_comm_world(self._h))
+
+    @property
+    def comm_rank(self) -> int:
+        return int(lib().mh_comm_rank(self._h))
+
+    def comm_broadcast(self, t, root=0):
+        self._check(lib().mh_comm_broadcast(self._h, _vp(t), C.c_uint64(t.numel() * t.element_size()), int(root)))
+        return t
+
+    def comm_allreduce_sum_f64(self, t):
+        assert t.dtype == self.torch.float64
+        self._check(lib().mh_comm_allreduce_sum_f64(self._h, _vp(t), C.c_uint64(t.numel())))
+        return t
+
+    def step_sharded(self, d_pts, d_aff, d_hyp, d_hyp_pt, d_best, d_labels, d_inliers, d_ref, events=None):
+        """one sharded hot pass (include/multih_b200.h: mh_step_sharded); `events` = two torch.cuda.Event recorded around K2"""
+        e0 = e1 = None
+        if events is not None:
+            e0, e1 = (C.c_void_p(e.cuda_event) for e in events)
+        self._check(lib().mh_step_sharded(self._h, _vp(d_pts), _vp(d_aff), C.c_int64(d_pts.shape[0]), _vp(d_hyp),
+                                          int(d_hyp.shape[0]), _vp(d_hyp_pt), _vp(d_best), _vp(d_labels), _vp(d_inliers),
+                                          _vp(d_ref), e0, e1))
+
+    def step_sharded_finish(self):
+        self._check(lib().mh_step_sharded_finish(self._h))
 
     def refit_3pt(self, d_pts, d_assign, Cn):
         t = self.torch

@@ -182,6 +182,8 @@ void mh_destroy(mh_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  mh_comm_destroy(ctx);
+  if (ctx->comm_acc) cudaFree(ctx->comm_acc);
   if (ctx->scratch) cudaFree(ctx->scratch);
   if (ctx->staging) cudaFree(ctx->staging);
   for (void* b : ctx->pbuf)

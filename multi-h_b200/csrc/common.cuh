@@ -67,6 +67,17 @@ struct mh_ctx {
   int32_t iterations = 0;
   double stage_ms[5] = {0, 0, 0, 0, 0};
   double alt_ms[5] = {0, 0, 0, 0, 0};   // inside the alternating optimisation: mean-shift, mode fit + inlier scan, data cost, graph cut, refit
+  // multi-GPU (comm.cu): NCCL communicator over the ranks that shard the correspondences, its own stream, and the double-buffered
+  // refit statistics whose all-reduce overlaps the next sharded pass
+  void* comm = nullptr;
+  int32_t comm_rank = 0, comm_world = 1;
+  cudaStream_t comm_stream = nullptr;
+  cudaEvent_t comm_ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  double* comm_acc = nullptr;
+  int32_t comm_acc_k = 0, comm_cur = 0, comm_pending = -1;
+  int32_t pend_K = 0;
+  void* pend_inliers = nullptr;
+  void* pend_ref = nullptr;
 };
 
 namespace mh {
@@ -149,6 +160,8 @@ mh_status launch_prefilter(mh_ctx*, const double* d_pts64, const double* d_aff64
 mh_status launch_modes_to_hyp(mh_ctx*, const double* d_modes, int C, float* d_hyp, double* d_hyp64 = nullptr);
 // FP64 members of the K2 family for the precise path (small N x K only): dataEnergy, inlier scan, single-H inliers
 mh_status launch_cost_dense64(mh_ctx*, const double* d_pts64, int64_t N, const double* d_hyp64, int K, int32_t* d_cost);
+mh_status launch_cost_list64(mh_ctx*, const double* d_pts64, int64_t N, const double* d_hyp64, int K, int kmax, uint32_t* d_list,
+                             int32_t* d_count);
 mh_status launch_inlier_stats64(mh_ctx*, const double* d_pts64, int64_t N, const double* d_hyp64, int K,
                                 double* d_scatter /*K x 6, pixel coords*/);
 mh_status launch_inliers_of64(mh_ctx*, const double* d_pts64, int64_t N, const double* d_hyp64_one, int idx,

@@ -1028,6 +1028,47 @@ mh_status launch_cost_dense64(mh_ctx* ctx, const double* d_pts64, int64_t N, con
   return MH_OK;
 }
 
+// Sparse-with-default form of the same costs for the labelling step: per site the (label, cost) entries with d2 < T, in
+// ascending label order, and their number; every label not listed costs cost_far, label 0 costs cost_outlier.  One warp per
+// site, lanes over the hypotheses, ballot-compacted — the entries are the dense kernel's values bit for bit (same expression).
+// entry = label << 16 | cost (the caller checks that both fit).  count may exceed kmax: the site's list is then incomplete.
+constexpr int LIST64_WARPS = 8;
+__global__ void __launch_bounds__(32 * LIST64_WARPS) cost_list64_kernel(const double* __restrict__ pts, long long N,
+                                                                        const double* __restrict__ hyp, int K, int kmax,
+                                                                        uint32_t* __restrict__ list, int32_t* __restrict__ count,
+                                                                        double lam, double T) {
+  const long long p = (long long)blockIdx.x * LIST64_WARPS + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (p >= N) return;
+  const double* q = pts + 4 * p;
+  const double x = q[0], y = q[1], x2 = q[2], y2 = q[3];
+  int n = 0;
+  for (int k0 = 0; k0 < K; k0 += 32) {
+    const int k = k0 + lane;
+    double d = T;
+    if (k < K) d = residual64(hyp + 9 * (size_t)k, x, y, x2, y2);
+    const bool in = k < K && d < T;
+    const unsigned m = __ballot_sync(0xffffffffu, in);
+    if (in) {
+      const int slot = n + __popc(m & ((1u << lane) - 1u));
+      if (slot < kmax) list[(size_t)p * kmax + slot] = ((uint32_t)(k + 1) << 16) | (uint32_t)(int)round(lam * (1.0 - d / T));
+    }
+    n += __popc(m);
+  }
+  if (lane == 0) count[p] = n;
+}
+
+mh_status launch_cost_list64(mh_ctx* ctx, const double* d_pts64, int64_t N, const double* d_hyp64, int K, int kmax, uint32_t* d_list,
+                             int32_t* d_count) {
+  if (N <= 0) return MH_OK;
+  const double thr2 = ctx->params.thr_homography * ctx->params.thr_homography, T = thr2 * 81.0 / 16.0;
+  const double lam = 100.0 / ctx->params.lambda;
+  cost_list64_kernel<<<(unsigned)((N + LIST64_WARPS - 1) / LIST64_WARPS), 32 * LIST64_WARPS, 0, ctx->stream>>>(d_pts64, N, d_hyp64, K, kmax,
+                                                                                                          d_list, d_count, lam, T);
+  MH_LAUNCHED(ctx, "cost_list64_kernel");
+  return MH_OK;
+}
+
 __global__ void __launch_bounds__(STATS_THREADS) inlier_stats64_kernel(const double* __restrict__ pts, long long N,
                                                                        const double* __restrict__ hyp, int K,
                                                                        double* __restrict__ scatter, double thr2) {

@@ -355,6 +355,7 @@ mh_status mh_process(mh_ctx* ctx, const double* pts, const double* aff, const do
   t0 = now_ms();
   std::vector<int32_t> labeling(N, -1), init(N), gc_labels(N);
   std::vector<int32_t> cost;
+  std::vector<uint32_t> sparse;   // per-site (label << 16 | cost) lists + counts of a labelling step
   MH_TRY(b_labels.alloc(ctx, sizeof(int32_t) * (uint64_t)N));
   double lastEnergy = (double)INT32_MAX;
   int not_changed_number = 0, iteration_number = 0;
@@ -437,11 +438,40 @@ mh_status mh_process(mh_ctx* ctx, const double* pts, const double* aff, const do
     const int L = K + 1;
     tm = now_ms();
     MH_TRY(upload_hyps(K));
-    MH_TRY(b_cost.alloc(ctx, sizeof(int32_t) * (uint64_t)N * L));
-    if (precise) MH_TRY(launch_cost_dense64(ctx, pts64, N, b_hyp64.as<double>(), K, b_cost.as<int32_t>()));
-    else MH_TRY(mh_data_cost_dense(ctx, b_pts.p, N, b_hyp.p, K, b_cost.p, 4));
     cost.resize((size_t)N * L);
-    MH_TRY(mh_memcpy_d2h(ctx, cost.data(), b_cost.p, sizeof(int32_t) * (size_t)N * L));
+    // The labelling step's data costs (dataEnergy, MultiH.cpp:473-504).  Precise path: sparse with default — the device lists
+    // the few (label, cost) entries with d2 < T per site (cost_list64_kernel), every other entry is one of two constants, so
+    // N x kmax words cross the bus instead of the N x (K + 1) matrix; the host solver indexes a dense matrix, which is filled
+    // here.  A site with more than kmax entries in range (rare) makes this step fall back to the dense matrix.
+    const int kmax = 32;
+    const double lam_d = 100.0 / P.lambda, T_d = P.thr_homography * P.thr_homography * 81.0 / 16.0;
+    const int c_out = (int)std::round(lam_d * T_d), c_far = 2 * c_out;
+    bool sparse_ok = precise && K < 65535 && lam_d < 65535.0 && K > kmax;
+    if (sparse_ok) {
+      MH_TRY(b_cost.alloc(ctx, sizeof(uint32_t) * (uint64_t)N * kmax + sizeof(int32_t) * (uint64_t)N));
+      uint32_t* d_list = b_cost.as<uint32_t>();
+      int32_t* d_cnt = reinterpret_cast<int32_t*>(d_list + (size_t)N * kmax);
+      MH_TRY(launch_cost_list64(ctx, pts64, N, b_hyp64.as<double>(), K, kmax, d_list, d_cnt));
+      sparse.resize((size_t)N * kmax + (size_t)N);
+      MH_TRY(mh_memcpy_d2h(ctx, sparse.data(), b_cost.p, sizeof(uint32_t) * sparse.size()));
+      const uint32_t* cnt = sparse.data() + (size_t)N * kmax;
+      for (int i = 0; i < N && sparse_ok; ++i) sparse_ok = cnt[i] <= (uint32_t)kmax;
+      if (sparse_ok) {
+        for (int i = 0; i < N; ++i) {
+          int32_t* row = cost.data() + (size_t)i * L;
+          row[0] = c_out;
+          std::fill(row + 1, row + L, c_far);
+          const uint32_t* e = sparse.data() + (size_t)i * kmax;
+          for (uint32_t k = 0; k < cnt[i]; ++k) row[e[k] >> 16] = (int32_t)(e[k] & 0xffffu);
+        }
+      }
+    }
+    if (!sparse_ok) {
+      MH_TRY(b_cost.alloc(ctx, sizeof(int32_t) * (uint64_t)N * L));
+      if (precise) MH_TRY(launch_cost_dense64(ctx, pts64, N, b_hyp64.as<double>(), K, b_cost.as<int32_t>()));
+      else MH_TRY(mh_data_cost_dense(ctx, b_pts.p, N, b_hyp.p, K, b_cost.p, 4));
+      MH_TRY(mh_memcpy_d2h(ctx, cost.data(), b_cost.p, sizeof(int32_t) * (size_t)N * L));
+    }
     const int32_t* init_ptr = nullptr;
     if (!changed) {  // warm start (MultiH.cpp:525-529)
       for (int i = 0; i < N; ++i) init[i] = std::min(std::max(labeling[i] + 1, 0), L - 1);

@@ -69,3 +69,20 @@ def test_two_rank_statistics_match_single_process(mh, orc):
     _, M10, n = orc.refit_haf(sc.pts, sc.aff, arg - 1, 5, sc.F)
     assert np.array_equal(acc[:, 10], n.astype(np.float64))
     assert np.allclose(acc[:, :10], M10, rtol=1e-12)         # all-reduce of refit statistics
+
+
+def test_comm_layer_argument_checks_and_nccl_binding(mh):
+    """csrc/comm.cu without a GPU: null arguments are refused, a null context reads as a single-rank world, and rank 0's
+    128-byte NCCL id is produced by the NCCL the process already has (torch's) — run-time binding, no link dependency."""
+    import ctypes as C
+
+    L = mh.capi.lib()
+    assert L.mh_comm_unique_id(None) == mh.capi.MH_EINVAL
+    assert L.mh_comm_world(None) == 1 and L.mh_comm_rank(None) == 0
+    assert L.mh_comm_init(None, None, 0, 1) == mh.capi.MH_EINVAL
+    assert L.mh_step_sharded_finish(None) == mh.capi.MH_EINVAL
+    buf = (C.c_char * 128)()
+    st = L.mh_comm_unique_id(buf)
+    assert st in (mh.capi.MH_OK, mh.capi.MH_ENCCL)   # ENCCL only where ncclGetUniqueId itself cannot run (no NCCL / no driver)
+    if st == mh.capi.MH_OK:
+        assert any(b != b"\x00" for b in buf)

@@ -793,3 +793,108 @@ def test_pipeline_equals_the_reference_source(mh, orc):
               f"outliers={(lab_r < 0).mean():.3f} sizes={np.bincount(lab_r[lab_r >= 0]).tolist()}")
         assert kept.sum() == len(lab_r) and K == len(H_r) and np.array_equal(lab[kept], lab_r)
         assert np.abs(H / H[:, 8:9] - H_r / H_r[:, 8:9]).max() <= 1e-6
+
+
+def _sharded_buffers(torch, n, K, dev):
+    return dict(hyp_pt=torch.empty((n, 12), dtype=torch.float32, device=dev), best=torch.empty(n, dtype=torch.int64, device=dev),
+                labels=torch.empty(n, dtype=torch.int32, device=dev), inliers=torch.empty(K, dtype=torch.int32, device=dev),
+                ref=torch.empty((K, 12), dtype=torch.float32, device=dev))
+
+
+def test_step_sharded_single_rank_equals_the_separate_calls_and_the_oracle(gpu_ctx, dev, scene, orc):
+    """mh_step_sharded without a communicator = K1 -> K2 fused -> labels -> K4 accumulate -> K4 solve of the separate entry
+    points, bit for bit; its labels are the oracle's data-term argmin and its refits the oracle's HAF refits."""
+    import torch
+
+    ctx = gpu_ctx
+    ctx.set_geometry(scene.F, scene.pts)
+    d_pts, d_aff = dev
+    n, K = d_pts.shape[0], 20
+    d_hyp = ctx.hypotheses_from_host(scene.planes)
+    b = _sharded_buffers(torch, n, K, d_pts.device)
+    for _ in range(3):      # repeated passes flip the double-buffered statistics: results must not depend on the parity
+        ctx.step_sharded(d_pts, d_aff, d_hyp, b["hyp_pt"], b["best"], b["labels"], b["inliers"], b["ref"])
+    ctx.step_sharded_finish()
+    torch.cuda.synchronize()
+    f = ctx.data_cost_fused(d_pts, d_hyp, kmax=0, want_list=False)
+    lab = torch.empty(n, dtype=torch.int32, device=d_pts.device)
+    ctx.labels_from_best(f["best"], lab)
+    ref = d_hyp.clone()
+    acc = ctx.refit_haf_accumulate(d_pts, d_aff, lab, K)
+    ctx.refit_haf_solve(acc, ref)
+    assert torch.equal(b["best"], f["best"]) and torch.equal(b["labels"], lab) and torch.equal(b["inliers"], f["inliers"])
+    assert torch.equal(b["ref"], ref) and torch.equal(b["hyp_pt"], ctx.haf_hypotheses(d_pts, d_aff))
+    _, arg, cnt = orc.data_cost_sweep(scene.pts, scene.planes)
+    assert (b["labels"].cpu().numpy() == arg - 1).mean() >= 0.9999       # FP32 evaluation: ties / threshold flips only
+    Ho, _, _ = orc.refit_haf(scene.pts, scene.aff, b["labels"].cpu().numpy(), K, scene.F, H_init=scene.planes)
+    assert _rel(ctx.hypotheses_to_host(b["ref"]), Ho).max() <= 1e-5
+
+
+def _sharded_worker(rank, world, port, n, K, seed, q):
+    import sys
+
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import torch
+    import torch.distributed as dist
+
+    import multih_b200 as m
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("gloo", rank=rank, world_size=world)     # carries only the 128-byte id: the data path is the library's NCCL
+    sc = m.scenes.make_scene(n, K, seed=seed)
+    lo, hi = m.dist.shard_range(n, rank, world)
+    ctx = m.Context(device=rank)
+    ctx.comm_init(rank, world)
+    assert (ctx.comm_rank, ctx.comm_world) == (rank, world)
+    ctx.set_geometry(sc.F, sc.pts)
+    d_pts, d_aff = ctx.upload(sc.pts[lo:hi], sc.aff[lo:hi])
+    dev = d_pts.device
+    d_hyp = ctx.hypotheses_from_host(sc.planes) if rank == 0 else torch.zeros((K, 12), dtype=torch.float32, device=dev)
+    b = _sharded_buffers(torch, hi - lo, K, dev)
+    for _ in range(3):
+        ctx.step_sharded(d_pts, d_aff, d_hyp, b["hyp_pt"], b["best"], b["labels"], b["inliers"], b["ref"])
+    ctx.step_sharded_finish()
+    torch.cuda.synchronize()
+    q.put((rank, lo, hi, d_hyp.cpu().numpy(), b["labels"].cpu().numpy(), b["inliers"].cpu().numpy(), b["ref"].cpu().numpy()))
+    dist.barrier()
+    ctx.comm_destroy()
+    ctx.close()
+    dist.destroy_process_group()
+
+
+def test_step_sharded_two_gpus_equals_one(mh, gpu_ctx):
+    """the library's own NCCL layer (mh_comm_init + mh_step_sharded) on 2 GPUs: broadcast hypotheses, concatenated labels,
+    all-reduced inlier counts and refit statistics reproduce the single-GPU pass (labels / counts exactly; refits to 1e-6:
+    the FP64 sums are associated differently)."""
+    import torch
+    import torch.multiprocessing as mp
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    n, K, seed = 30001, 12, 77
+    mpc = mp.get_context("spawn")
+    q = mpc.Queue()
+    port = 29700 + os.getpid() % 1500
+    procs = [mpc.Process(target=_sharded_worker, args=(r, 2, port, n, K, seed, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = sorted((q.get(timeout=300) for _ in range(2)), key=lambda t: t[0])
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    sc = mh.scenes.make_scene(n, K, seed=seed)
+    ctx = gpu_ctx
+    ctx.set_geometry(sc.F, sc.pts)
+    d_pts, d_aff = ctx.upload(sc.pts, sc.aff)
+    d_hyp = ctx.hypotheses_from_host(sc.planes)
+    b = _sharded_buffers(torch, n, K, d_pts.device)
+    ctx.step_sharded(d_pts, d_aff, d_hyp, b["hyp_pt"], b["best"], b["labels"], b["inliers"], b["ref"])
+    ctx.step_sharded_finish()
+    torch.cuda.synchronize()
+    assert np.array_equal(got[1][3], d_hyp.cpu().numpy())                                         # broadcast
+    assert np.array_equal(np.concatenate([g[4] for g in got]), b["labels"].cpu().numpy())         # shards = scene
+    for g in got:
+        assert np.array_equal(g[5], b["inliers"].cpu().numpy())                                   # whole-scene counts on every rank
+        np.testing.assert_allclose(g[6], b["ref"].cpu().numpy(), rtol=1e-5, atol=1e-6)
+    assert np.array_equal(got[0][6], got[1][6])                                                   # ranks agree bit for bit
