@@ -450,6 +450,15 @@ __global__ void __launch_bounds__(256) cost_argmin_wild_kernel(const float4* __r
   }
 }
 
+// the side pass as a launcher (also used by k2_tmem.cu)
+mh_status launch_cost_argmin_wild(mh_ctx* ctx, const float4* d_pts, int64_t N, const float* d_hyp, const int* d_wild_count,
+                                  const int* d_wild_list, const CostParams& cp, const FastOut& fo) {
+  const unsigned wild_grid = (unsigned)std::min<long long>((N + 255) / 256, 8LL * ctx->sm_count);
+  cost_argmin_wild_kernel<<<wild_grid, 256, 0, ctx->stream>>>(d_pts, N, d_hyp, d_wild_count, d_wild_list, cp, fo);
+  MH_LAUNCHED(ctx, "cost_argmin_wild_kernel");
+  return MH_OK;
+}
+
 template <bool COUNT_INLIERS, int WARPS, int MINB, int PB, int CH, bool PIPE, int QTHR = 0>
 static mh_status launch_tc(mh_ctx* ctx, const float4* d_pts, int64_t N, const float* d_hyp, int K, const CostParams& cp,
                            const FastOut& fo) {

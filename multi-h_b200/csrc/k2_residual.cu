@@ -796,6 +796,8 @@ __global__ void fused_init_kernel(long long N, int K, int32_t* list_count, u64* 
 
 mh_status launch_cost_argmin_tc(mh_ctx* ctx, const float4* d_pts, int64_t N, const float* d_hyp, int K, const CostParams& cp,
                                 const FastOut& fo, int config);  // k2_mma.cu
+mh_status launch_cost_argmin_tmem(mh_ctx* ctx, const float4* d_pts, int64_t N, const float* d_hyp, int K, const CostParams& cp,
+                                  const FastOut& fo, int config);  // k2_tmem.cu
 
 int g_fused_variant = 1;  // 1 = packed FFMA2 (default), 0 = scalar FFMA (A/B evidence)
 int g_fast_config = 55;   // fast-path variant, see launch_cost_fused / launch_cost_argmin_tc; 55 = v7 tensor-core kernel, 4 warps x 5 CTAs/SM x 48 rows/warp (default); 5 = v3 FFMA2 kernel
@@ -882,7 +884,8 @@ mh_status launch_cost_fused(mh_ctx* ctx, const float4* d_pts, int64_t N, const f
     };
 #endif
     if (K >= 65535 || cp.cost_outlier > 0xffff) g_fast_config = std::min(g_fast_config, 6);  // the tensor-core kernel packs (cost, label) in 32 bits
-    if (g_fast_config >= 30 && g_fast_config < 100) return launch_cost_argmin_tc(ctx, d_pts, N, d_hyp, K, cp, fo, g_fast_config);
+    if (g_fast_config >= 70 && g_fast_config < 100) return launch_cost_argmin_tmem(ctx, d_pts, N, d_hyp, K, cp, fo, g_fast_config);
+    if (g_fast_config >= 30 && g_fast_config < 70) return launch_cost_argmin_tc(ctx, d_pts, N, d_hyp, K, cp, fo, g_fast_config);
     switch (g_fast_config) {
 #ifdef MH_TUNING
       case 20: MH_TRY(launch_m(cost_argmin_mma_kernel<true, 2, 2>, cost_argmin_mma_kernel<false, 2, 2>, 2)); break;

@@ -898,3 +898,36 @@ def test_step_sharded_two_gpus_equals_one(mh, gpu_ctx):
         assert np.array_equal(g[5], b["inliers"].cpu().numpy())                                   # whole-scene counts on every rank
         np.testing.assert_allclose(g[6], b["ref"].cpu().numpy(), rtol=1e-5, atol=1e-6)
     assert np.array_equal(got[0][6], got[1][6])                                                   # ranks agree bit for bit
+
+
+@pytest.mark.parametrize("config", [76, 77])
+def test_k2_tcgen05_variant_is_bit_exact(mh, config):
+    """K2 v8 (csrc/k2_tmem.cu: tcgen05.mma kind::tf32 into TMEM, tcgen05.ld epilogue) is the A/B partner of the default mma.sync
+    kernel: (cost, label) equal the dense matrix's argmin bit for bit, wild / non-finite hypotheses included, inlier counts inside
+    the residual tolerance band; also with the hypothesis range split over CTAs (few correspondences)."""
+    import torch
+
+    sc = mh.scenes.make_scene(50_000, 40, seed=0xB200 + 21)
+    ctx = mh.Context()
+    ctx.set_geometry(sc.F, sc.pts)
+    d_pts, d_aff = ctx.upload(sc.pts, sc.aff)
+    d_h = ctx.haf_hypotheses(d_pts, d_aff)
+    g = torch.Generator("cuda").manual_seed(5)
+    idx = torch.randint(0, 50_000, (1001,), device="cuda", generator=g)
+    hyp = torch.cat([ctx.hypotheses_from_host(sc.planes), d_h[idx]]).contiguous()        # K = 1041: ragged last chunk
+    hyp[100, :9] *= torch.tensor([50, 50, 50, 1, 1, 1, 1, 1, 1], device="cuda")
+    hyp[101, 8] = 1e-9
+    hyp[102, 4] = float("nan")
+    try:
+        ctx.set_fast_config(config)
+        for pts in (d_pts, d_pts[:3001].contiguous()):
+            f = ctx.data_cost_fused(pts, hyp, kmax=0, want_list=False, out={})
+            dense = ctx.data_cost_dense(pts, hyp)
+            assert torch.equal(f["best"] & 0xFFFFFFFF, dense.argmin(1))
+            assert torch.equal(f["best"] >> 32, dense.min(1).values.to(torch.int64))
+            ref, band = _inlier_reference(ctx, pts, hyp)
+            assert bool(((f["inliers"] - ref).abs() <= band).all())
+            f2 = ctx.data_cost_fused(pts, hyp, kmax=0, want_list=False, want_inliers=False, out={})
+            assert torch.equal(f2["best"], f["best"])
+    finally:
+        ctx.set_fast_config(55)
