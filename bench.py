@@ -253,7 +253,19 @@ def main():
     d_ref = torch.empty((K_HYP, 12), dtype=torch.float32, device=dev)
     h_labels = torch.empty(n_loc, dtype=torch.int32).pin_memory()
     h_ref = torch.empty((K_HYP, 12), dtype=torch.float32).pin_memory()
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    # L2 policy (timing rule: flush L2 between timed iterations OR use inputs larger than L2): no flush — consecutive steps read
+    # DIFFERENT resident copies of the rank's inputs and write their own outputs; the copies of one rotation total >= 2 x L2, so
+    # by the time a copy comes round again the chip has streamed more than two L2s of other inputs (plus all outputs) through it.
+    l2_bytes = int(getattr(torch.cuda.get_device_properties(dev), "L2_cache_size", 126 << 20))
+    in_bytes = (d_pts.numel() + d_aff.numel()) * 4
+    n_sets = max(2, -(-2 * l2_bytes // max(in_bytes, 1)))
+    sets = [{"pts": d_pts, "aff": d_aff, "hyp_pt": d_hyp_pt, "best": fused["best"], "labels": labels}]
+    for _ in range(n_sets - 1):
+        sets.append({"pts": d_pts.clone(), "aff": d_aff.clone(), "hyp_pt": torch.empty_like(d_hyp_pt),
+                     "best": torch.empty_like(fused["best"]), "labels": torch.empty_like(labels)})
+    l2_note = (f"no flush: consecutive steps read different resident copies of the rank's inputs, {n_sets} x {in_bytes / 2**20:.0f} MiB "
+               f"per rotation >= 2 x {l2_bytes / 2**20:.0f} MiB L2, and write their own outputs")
+    step_no = [0]
     k2_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
              for _ in range(args.steps + args.warmup + 1)]
 
@@ -272,7 +284,9 @@ def main():
         ctx.step_sharded_finish()
 
     def hot_pass(ev=None):
-        ctx.step_sharded(d_pts, d_aff, d_hyp, d_hyp_pt, fused["best"], labels, fused["inliers"], d_ref, events=ev)
+        b = sets[step_no[0] % n_sets]
+        step_no[0] += 1
+        ctx.step_sharded(b["pts"], b["aff"], d_hyp, b["hyp_pt"], b["best"], b["labels"], fused["inliers"], d_ref, events=ev)
 
     def stats_and_refit():
         """e2e ordering (K2 before K1): labels -> K4 statistics -> all-reduce -> solves, in stream order"""
@@ -316,7 +330,6 @@ def main():
     # ---- device-resident timing ------------------------------------------------------------------------------------------
     for i in range(args.warmup):
         hot_pass(k2_ev[i])
-        flush.zero_()
     finish_pending()
     barrier()
     sampler = ClockSampler(local)
@@ -335,7 +348,6 @@ def main():
     t0.record()
     for i in range(args.steps):
         hot_pass(k2_ev[args.warmup + i])
-        flush.zero_()  # L2 flush between timed iterations (inside the timed region; ~40 us per step)
     finish_pending()
     t1.record()
     barrier()
@@ -569,7 +581,7 @@ def main():
         "config": {"workload": WORKLOAD,
                    "correspondences": n_total, "hypotheses": K_HYP, "per_rank": n_loc,
                    "step": "K1 HAF + K2 fused cost/argmin/inlier-count + K4 refit (+ NCCL bcast/all-reduce for N>1)",
-                   "l2": "256 MiB memset between steps, inside the timed region"},
+                   "l2": l2_note},
         "clocks": sampler.summary(),
         "e2e": {"value": e2e_value, "unit": "residuals/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": float(te[0]) / args.steps},

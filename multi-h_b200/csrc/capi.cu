@@ -133,6 +133,8 @@ void sym_eigen3_host(const double* A, double* w, double* Vrows) { sym_eigen3(A, 
 
 using namespace mh;
 
+extern "C" void mh_step_release(mh_ctx* ctx);   // comm.cu (internal)
+
 extern "C" {
 
 const char* mh_version(void) { return "multih_b200 0.1 (sm_100a)"; }
@@ -183,6 +185,7 @@ void mh_destroy(mh_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   mh_comm_destroy(ctx);
+  mh_step_release(ctx);
   if (ctx->comm_acc) cudaFree(ctx->comm_acc);
   if (ctx->scratch) cudaFree(ctx->scratch);
   if (ctx->staging) cudaFree(ctx->staging);

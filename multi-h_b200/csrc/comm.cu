@@ -3,7 +3,7 @@
 // communicator.  Correspondences are sharded over the ranks, hypotheses are
 // replicated; a sharded hot pass is
 //     ncclBroadcast  hypotheses K x 12 FP32 from rank 0         (overlaps K1 on a second stream)
-//     K1 per-correspondence HAF, K2 fused cost / argmin / inlier counts on the local shard
+//     K2 fused cost / argmin / inlier counts on the local shard; K1 per-correspondence HAF behind it on a second stream (fills K2's tail)
 //     K4 refit statistics of the local shard, inlier counts packed into their pad column
 //     ncclAllReduce(sum) of the K x 12 FP64 statistics           (overlaps the NEXT pass: double-buffered)
 //     K4 batched eigen-solves, redundantly on every rank.
@@ -120,6 +120,13 @@ mh_status mh_comm_destroy(mh_ctx* ctx) {
   return MH_OK;
 }
 
+void mh_step_release(mh_ctx* ctx) {   // called by mh_destroy: the second stream of mh_step_sharded
+  if (!ctx) return;
+  if (ctx->aux_stream) { cudaStreamSynchronize(ctx->aux_stream); cudaStreamDestroy(ctx->aux_stream); ctx->aux_stream = nullptr; }
+  for (cudaEvent_t& e : ctx->aux_ev)
+    if (e) { cudaEventDestroy(e); e = nullptr; }
+}
+
 int32_t mh_comm_rank(const mh_ctx* ctx) { return ctx ? ctx->comm_rank : 0; }
 int32_t mh_comm_world(const mh_ctx* ctx) { return ctx ? ctx->comm_world : 1; }
 
@@ -172,21 +179,43 @@ mh_status mh_step_sharded(mh_ctx* ctx, const void* d_pts, const void* d_aff, int
   }
   const int b = ctx->comm_cur;
   double* acc = ctx->comm_acc + (size_t)b * 12 * ctx->comm_acc_k;
-  if (multi) {   // hypotheses from rank 0, on the communication stream, while K1 runs
-    MH_CUDA(ctx, cudaEventRecord(ctx->comm_ev[0], ctx->stream));
-    MH_CUDA(ctx, cudaStreamWaitEvent(ctx->comm_stream, ctx->comm_ev[0], 0));
+  if (!ctx->aux_stream) {
+    MH_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking));
+    for (cudaEvent_t& e : ctx->aux_ev) MH_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  }
+  MH_CUDA(ctx, cudaEventRecord(ctx->aux_ev[0], ctx->stream));   // everything before this pass (inputs uploaded, previous pass done)
+  if (multi) {   // hypotheses from rank 0, on the communication stream
+    MH_CUDA(ctx, cudaStreamWaitEvent(ctx->comm_stream, ctx->aux_ev[0], 0));
     MH_NCCL(ctx, a.Broadcast(d_hyp, d_hyp, (size_t)K * 12, kNcclFloat32, 0, (NcclComm)ctx->comm, ctx->comm_stream));
     MH_CUDA(ctx, cudaEventRecord(ctx->comm_ev[1], ctx->comm_stream));
+    MH_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->comm_ev[1], 0));   // K2 needs the hypotheses
   }
-  MH_TRY(launch_haf(ctx, (const float4*)d_pts, (const float4*)d_aff, n_local, (float*)d_hyp_pt, 0));                     // K1
-  if (multi) MH_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->comm_ev[1], 0));
+  // K1 depends on nothing in this pass and nothing in it depends on K1, so it runs on a second stream.  One GPU: it starts when
+  // K2 has finished and runs beside the K4 chain (label CSR, segmented statistics: small, latency-bound grids that leave most SMs
+  // idle) — K2 itself keeps the chip to itself, which also keeps its event-timed duration (the roofline figure) clean.  Several
+  // GPUs: it is enqueued first and runs under the hypothesis broadcast that K2 has to wait for.  The pass's stream joins it
+  // before the solves.
+  auto k1_on_second_stream = [&]() -> mh_status {
+    cudaStream_t main_stream = ctx->stream;
+    if (!multi) MH_CUDA(ctx, cudaEventRecord(ctx->aux_ev[0], ctx->stream));   // K2 done
+    MH_CUDA(ctx, cudaStreamWaitEvent(ctx->aux_stream, ctx->aux_ev[0], 0));
+    ctx->stream = ctx->aux_stream;
+    const mh_status st = launch_haf(ctx, (const float4*)d_pts, (const float4*)d_aff, n_local, (float*)d_hyp_pt, 0);       // K1
+    ctx->stream = main_stream;
+    if (st != MH_OK) return st;
+    MH_CUDA(ctx, cudaEventRecord(ctx->aux_ev[1], ctx->aux_stream));
+    return MH_OK;
+  };
+  if (multi) MH_TRY(k1_on_second_stream());
   if (ev_k2_begin) MH_CUDA(ctx, cudaEventRecord((cudaEvent_t)ev_k2_begin, ctx->stream));
   MH_TRY(launch_cost_fused(ctx, (const float4*)d_pts, n_local, (const float*)d_hyp, K, 0, nullptr, nullptr,
                            (unsigned long long*)d_best, (int32_t*)d_inliers));                                             // K2
   if (ev_k2_end) MH_CUDA(ctx, cudaEventRecord((cudaEvent_t)ev_k2_end, ctx->stream));
+  if (!multi) MH_TRY(k1_on_second_stream());
   MH_TRY(launch_labels_from_best(ctx, (const unsigned long long*)d_best, n_local, (int32_t*)d_labels));
   MH_CUDA(ctx, cudaMemcpyAsync(d_ref, d_hyp, sizeof(float) * 12 * (size_t)K, cudaMemcpyDeviceToDevice, ctx->stream));     // labels without members keep theirs
   MH_TRY(launch_refit_haf_accumulate(ctx, (const float4*)d_pts, (const float4*)d_aff, (const int32_t*)d_labels, n_local, K, acc));   // K4 statistics
+  MH_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->aux_ev[1], 0));                                                       // K1 joined
   if (!multi) return launch_refit_haf_solve(ctx, acc, K, (float*)d_ref, nullptr);
   if (d_inliers) MH_TRY(launch_pack_inlier_counts(ctx, (int32_t*)d_inliers, K, acc, 0));
   MH_CUDA(ctx, cudaEventRecord(ctx->comm_ev[0], ctx->stream));

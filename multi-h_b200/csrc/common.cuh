@@ -78,6 +78,8 @@ struct mh_ctx {
   int32_t pend_K = 0;
   void* pend_inliers = nullptr;
   void* pend_ref = nullptr;
+  cudaStream_t aux_stream = nullptr;   // mh_step_sharded: K1 runs here, behind K2
+  cudaEvent_t aux_ev[2] = {nullptr, nullptr};
 };
 
 namespace mh {

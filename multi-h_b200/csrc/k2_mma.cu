@@ -21,6 +21,8 @@
 // Per-correspondence argmin state is replicated in the 4 lanes of a quad and kept
 // coherent by a quad min-reduce inside the update.
 // ============================================================================
+#include <cstdlib>
+
 #include "k2_device.cuh"
 
 namespace mh {
@@ -116,7 +118,7 @@ template <bool COUNT_INLIERS, int WARPS, int MINB, int PB, int CH, bool PIPE, in
 __global__ void __launch_bounds__(WARPS * 32, MINB)
 cost_argmin_tc_kernel(const float4* __restrict__ pts, long long N, const float* __restrict__ hyp,
                       const float2* __restrict__ hsplit, int K, int k_per_block, CostParams cp, FastOut o,
-                      int use_atomic_best) {
+                      int use_atomic_best, int tiles_full, int tail_split, int kpb_tail) {
   constexpr int THREADS = WARPS * 32;
   constexpr unsigned CHUNK_BYTES = CH * 96;
   constexpr bool DEFER = QTHR > 0;
@@ -134,9 +136,19 @@ cost_argmin_tc_kernel(const float4* __restrict__ pts, long long N, const float* 
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
   constexpr int PTS_PER_WARP = 16 * PB, TILE = WARPS * PTS_PER_WARP;
-  const long long tile0 = (long long)blockIdx.x * TILE + (long long)warp * PTS_PER_WARP;
-  const int kbeg = blockIdx.y * k_per_block;          // multiple of CH
-  const int kend = min(K, kbeg + k_per_block);
+  // Tail wave: the CTAs beyond the last full wave (blockIdx.x >= tiles_full) each take 1 / tail_split of the hypothesis range
+  // of their tile, so the last, partly filled wave ends after ceil(tail tiles * split / slots) / split of a wave instead of a
+  // whole one; their results merge through the same atomics as a K-split launch.
+  int tile_idx = blockIdx.x, kbeg = blockIdx.y * k_per_block;          // kbeg: multiple of CH
+  int kend = min(K, kbeg + k_per_block);
+  if (tail_split > 1 && (int)blockIdx.x >= tiles_full) {
+    const int part = blockIdx.x - tiles_full;
+    tile_idx = tiles_full + part / tail_split;
+    kbeg = (part % tail_split) * kpb_tail;
+    kend = min(K, kbeg + kpb_tail);
+    use_atomic_best = 1;
+  }
+  const long long tile0 = (long long)tile_idx * TILE + (long long)warp * PTS_PER_WARP;
   const int nchunks = (kend - kbeg + CH - 1) / CH;    // hsplit is padded to whole chunks
 
   if (threadIdx.x == 0) {
@@ -471,7 +483,28 @@ static mh_status launch_tc(mh_ctx* ctx, const float4* d_pts, int64_t N, const fl
   int kpb = (K + ks - 1) / ks;
   kpb = ((kpb + CH - 1) / CH) * CH;   // whole chunks per CTA
   ks = (K + kpb - 1) / kpb;
-  const int Kpad = ks * kpb;
+  int Kpad = ks * kpb;
+  // multi-wave launches: split the hypothesis range of the tiles of the last, partial wave (see the kernel)
+  int tiles_full = (int)tiles, tail_split = 1, kpb_tail = kpb;
+  unsigned grid_x = tiles;
+  const int slots = MINB * ctx->sm_count;
+  static const bool tail_on = !(std::getenv("MH_TAIL_SPLIT") && std::atoi(std::getenv("MH_TAIL_SPLIT")) == 0);   // measurement aid
+  if (tail_on && ks == 1 && (int)tiles > slots && tiles % slots != 0) {
+    const int tail = (int)(tiles % slots);
+    double best_t = 1.0;
+    for (int sp = 2; sp <= 16 && sp * CH <= K; sp *= 2) {
+      const int kp = (((K + sp - 1) / sp + CH - 1) / CH) * CH;
+      if ((sp - 1) * kp >= K) continue;   // every part must own at least one hypothesis
+      const double t = (double)((tail * sp + slots - 1) / slots) / sp + 0.01 * sp;   // + a small per-part overhead
+      if (t < best_t - 1e-9) { best_t = t; tail_split = sp; }
+    }
+    if (tail_split > 1) {
+      tiles_full = (int)tiles - tail;
+      kpb_tail = (((K + tail_split - 1) / tail_split + CH - 1) / CH) * CH;
+      Kpad = std::max(Kpad, tail_split * kpb_tail);
+      grid_x = (unsigned)tiles_full + (unsigned)tail * (unsigned)tail_split;
+    }
+  }
   // scratch: [Kpad x 96 B split fragments][wild count (16 B)][K wild indices]
   MH_TRY(ensure_scratch(ctx, (uint64_t)Kpad * 96 + 16 + (uint64_t)K * 4));
   float2* d_split = (float2*)ctx->scratch;
@@ -484,7 +517,8 @@ static mh_status launch_tc(mh_ctx* ctx, const float4* d_pts, int64_t N, const fl
   const size_t smem = 2 * (size_t)CH * 96 + 2 * (size_t)WARPS * CH + 16 + (QTHR > 0 ? (size_t)WARPS * (queue_capacity(PB) + 16 * PB) * 4 : 0);
   auto kern = cost_argmin_tc_kernel<COUNT_INLIERS, WARPS, MINB, PB, CH, PIPE, QTHR>;
   MH_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<dim3(tiles, (unsigned)ks), WARPS * 32, smem, ctx->stream>>>(d_pts, N, d_hyp, d_split, K, kpb, cp, fo, ks > 1);
+  kern<<<dim3(grid_x, (unsigned)ks), WARPS * 32, smem, ctx->stream>>>(d_pts, N, d_hyp, d_split, K, kpb, cp, fo, ks > 1, tiles_full, tail_split,
+                                                                      kpb_tail);
   MH_LAUNCHED(ctx, "cost_argmin_tc_kernel");
   const unsigned wild_grid = (unsigned)std::min<long long>((N + 255) / 256, 8LL * ctx->sm_count);
   cost_argmin_wild_kernel<<<wild_grid, 256, 0, ctx->stream>>>(d_pts, N, d_hyp, d_wild_count, d_wild_list, cp, fo);

@@ -9,7 +9,7 @@ def ev_time(fn, reps=5, warm=2):
     for _ in range(reps): fn()
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / reps
-N = 1 << 20
+N = int(os.environ.get("TUNE_N", str(1 << 20)))
 scb = m.scenes.make_scene(N, 200, seed=0xB200 + 3)
 ctx = m.Context(); ctx.set_geometry(scb.F, scb.pts); pb, ab = ctx.upload(scb.pts, scb.aff)
 hb = ctx.haf_hypotheses(pb, ab)
