@@ -60,6 +60,10 @@ __device__ __forceinline__ int cost_of(float d2, const CostParams& cp) {
 struct FastOut {
   u64* best;             // [N] packed (cost << 32 | label), pre-initialised to (cost_outlier << 32 | 0)
   int32_t* inlier_count; // [K]
+  // list-producing members only (zero otherwise): per site up to kmax entries (label << 8 | cost) with d2 < T, and their number
+  uint32_t* list;        // [N][kmax]
+  int32_t* list_count;   // [N], pre-initialised to 0
+  int kmax;
 };
 
 __device__ __forceinline__ void fast_thresholds(int best_cost, const CostParams& cp, float& negmid, float& half) {

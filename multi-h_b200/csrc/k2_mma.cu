@@ -114,7 +114,11 @@ struct Acc {
 // add (2 blocks x 2 PB row slots x 32 lanes): no capacity test on the push path, and one inlined copy of the drain.
 __host__ __device__ constexpr int queue_capacity(int PB) { return 32 + 2 * 2 * PB * 32; }
 
-template <bool COUNT_INLIERS, int WARPS, int MINB, int PB, int CH, bool PIPE, int QTHR = 0>
+// LIST: the same kernel as the producer of sparse per-site cost lists — what a labeller consumes (mh_data_cost_fused with d_list).
+// The filter is the constant interval 0 <= d2 < T (never tightened), every candidate pair goes through the queue, and the drain
+// appends (label << 8 | cost) to the site's list (slot from a shared-memory counter per row; from the global counter when several
+// CTAs share a row) next to the argmin update.  Entries are in drain order, not label order.
+template <bool COUNT_INLIERS, int WARPS, int MINB, int PB, int CH, bool PIPE, int QTHR = 0, bool LIST = false>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
 cost_argmin_tc_kernel(const float4* __restrict__ pts, long long N, const float* __restrict__ hyp,
                       const float2* __restrict__ hsplit, int K, int k_per_block, CostParams cp, FastOut o,
@@ -124,14 +128,17 @@ cost_argmin_tc_kernel(const float4* __restrict__ pts, long long N, const float* 
   constexpr bool DEFER = QTHR > 0;
   constexpr int QCAP = queue_capacity(PB);
   static_assert(QTHR <= 32, "queue_capacity() assumes at most 32 waiting entries");
+  static_assert(!LIST || DEFER, "the list member appends from the deferred queue");
+  constexpr int WSTRIDE = QCAP + 16 * PB * (LIST ? 2 : 1);   // per warp: queue | packed best per row | LIST: entries per row
   // dynamic shared memory: [2][CH][3][4] float2 split fragments | [2][WARPS][CH] u8 per-warp inlier counts | 2 mbarriers
   //                        | DEFER: [WARPS][QCAP] candidate queues | [WARPS][16 PB] packed (cost << 16 | label) per row
   extern __shared__ __align__(128) unsigned char tc_smem[];
   float2* sB = reinterpret_cast<float2*>(tc_smem);
   unsigned char* sCnt = tc_smem + 2 * CHUNK_BYTES;
   unsigned long long* bars = reinterpret_cast<unsigned long long*>(tc_smem + 2 * CHUNK_BYTES + 2 * WARPS * CH);
-  unsigned* sQ = reinterpret_cast<unsigned*>(tc_smem + 2 * CHUNK_BYTES + 2 * WARPS * CH + 16) + (threadIdx.x >> 5) * (QCAP + 16 * PB);
+  unsigned* sQ = reinterpret_cast<unsigned*>(tc_smem + 2 * CHUNK_BYTES + 2 * WARPS * CH + 16) + (threadIdx.x >> 5) * WSTRIDE;
   unsigned* sBest = sQ + QCAP;
+  unsigned* sRowCnt = sBest + 16 * PB;   // LIST only
   int qcnt = 0;   // warp-uniform
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
@@ -170,7 +177,13 @@ cost_argmin_tc_kernel(const float4* __restrict__ pts, long long N, const float* 
   float NX2[PB][2], NY2[PB][2], CM[PB][2], HALF[PB][2];
   auto set_filter = [&](int best_cost, float& cm, float& half) {
     float negmid;
-    fast_thresholds(best_cost, cp, negmid, half);
+    if (LIST) {   // every residual below the truncation threshold is a list entry: 0 <= d2 < 1.001 T, whatever the best so far
+      const float hi = cp.T * 1.001f;
+      negmid = -0.5f * hi;
+      half = 0.5f * hi * 1.000001f + 1e-30f;
+    } else {
+      fast_thresholds(best_cost, cp, negmid, half);
+    }
     cm = COUNT_INLIERS ? cp.thr2 + negmid : negmid;
   };
   unsigned BEST[PB][2];
@@ -193,7 +206,10 @@ cost_argmin_tc_kernel(const float4* __restrict__ pts, long long N, const float* 
     }
   const u64 ONE2 = pk(1.f, 1.f), NEGTHR2 = pk(-cp.thr2, -cp.thr2);
   if (DEFER) {
-    for (int i = lane; i < 16 * PB; i += 32) sBest[i] = best_init;
+    for (int i = lane; i < 16 * PB; i += 32) {
+      sBest[i] = best_init;
+      if (LIST) sRowCnt[i] = 0u;
+    }
     __syncwarp();
   }
 
@@ -261,19 +277,39 @@ cost_argmin_tc_kernel(const float4* __restrict__ pts, long long N, const float* 
       unsigned mine = 0xffffffffu;
       if (ih0 < kend && da < cp.T) mine = ((unsigned)cost_in_range(da, cp) << 16) | (unsigned)(ih0 + 1);
       if (ih0 + 1 < kend && db < cp.T) mine = min(mine, ((unsigned)cost_in_range(db, cp) << 16) | (unsigned)(ih0 + 2));
+      if (LIST) {
+        const long long idx = tile0 + row;
+#pragma unroll
+        for (int which = 0; which < 2; ++which) {
+          const float d = which ? db : da;
+          // a wild hypothesis (off the tensor cores, see split_hyp_tf32_kernel) is listed by cost_argmin_wild_kernel; it shows up
+          // here when its pair partner raised the flag
+          const float* hh = which ? hb : ha;
+          float mx = 0.f;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) mx = fmaxf(mx, fabsf(hh[k]));
+          const bool wild = !(mx <= WILD_RATIO * fabsf(hh[8])) || !(fabsf(hh[8]) < 3.0e38f);
+          if (!wild && ih0 + which < kend && d < cp.T) {
+            const int slot = use_atomic_best ? atomicAdd(o.list_count + idx, 1) : (int)atomicAdd(sRowCnt + row, 1u);
+            if (slot < o.kmax) o.list[idx * o.kmax + slot] = ((unsigned)(ih0 + which + 1) << 8) | (unsigned)cost_in_range(d, cp);
+          }
+        }
+      }
       if (mine != 0xffffffffu) atomicMin(sBest + row, mine);   // (cost, label) packed: ties keep the lowest label
     }
     __syncwarp();
+    if (!LIST) {
 #pragma unroll
-    for (int pb = 0; pb < PB; ++pb)
+      for (int pb = 0; pb < PB; ++pb)
 #pragma unroll
-      for (int r = 0; r < 2; ++r) {
-        const unsigned b = sBest[pb * 16 + g + 8 * r];
-        if (b < BEST[pb][r]) {
-          BEST[pb][r] = b;
-          set_filter((int)(b >> 16), CM[pb][r], HALF[pb][r]);
+        for (int r = 0; r < 2; ++r) {
+          const unsigned b = sBest[pb * 16 + g + 8 * r];
+          if (b < BEST[pb][r]) {
+            BEST[pb][r] = b;
+            set_filter((int)(b >> 16), CM[pb][r], HALF[pb][r]);
+          }
         }
-      }
+    }
     qcnt = 0;
   };
 
@@ -412,13 +448,22 @@ cost_argmin_tc_kernel(const float4* __restrict__ pts, long long N, const float* 
     }
   }
   if (DEFER && qcnt > 0) drain();
+  if (LIST && t == 0 && !use_atomic_best) {
+#pragma unroll
+    for (int pb = 0; pb < PB; ++pb)
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const long long idx = tile0 + pb * 16 + g + 8 * r;
+        if (idx < N) o.list_count[idx] = (int)sRowCnt[pb * 16 + g + 8 * r];
+      }
+  }
   if (o.best && t == 0) {  // the quad holds identical state: lane t == 0 writes
 #pragma unroll
     for (int pb = 0; pb < PB; ++pb)
 #pragma unroll
       for (int r = 0; r < 2; ++r) {
         const long long idx = tile0 + pb * 16 + g + 8 * r;
-        const unsigned b = BEST[pb][r];
+        const unsigned b = LIST ? sBest[pb * 16 + g + 8 * r] : BEST[pb][r];
         if (idx < N && (b & 0xffffu) != 0u) {
           const u64 v = ((u64)(b >> 16) << 32) | (u64)(b & 0xffffu);
           if (use_atomic_best) atomicMin(o.best + idx, v);
@@ -452,6 +497,10 @@ __global__ void __launch_bounds__(256) cost_argmin_wild_kernel(const float4* __r
       if (live && d2 < cp.T) {
         const unsigned c = (unsigned)cost_in_range(d2, cp);
         if (c < bc || (c == bc && (unsigned)(k + 1) < bl)) { bc = c; bl = (unsigned)(k + 1); }   // list order is arbitrary
+        if (o.list) {
+          const int slot = atomicAdd(o.list_count + idx, 1);
+          if (slot < o.kmax) o.list[idx * o.kmax + slot] = ((unsigned)(k + 1) << 8) | c;
+        }
       }
       if (o.inlier_count) {
         const unsigned m = __ballot_sync(0xffffffffu, live && d2 < cp.thr2);
@@ -471,7 +520,7 @@ mh_status launch_cost_argmin_wild(mh_ctx* ctx, const float4* d_pts, int64_t N, c
   return MH_OK;
 }
 
-template <bool COUNT_INLIERS, int WARPS, int MINB, int PB, int CH, bool PIPE, int QTHR = 0>
+template <bool COUNT_INLIERS, int WARPS, int MINB, int PB, int CH, bool PIPE, int QTHR = 0, bool LIST = false>
 static mh_status launch_tc(mh_ctx* ctx, const float4* d_pts, int64_t N, const float* d_hyp, int K, const CostParams& cp,
                            const FastOut& fo) {
   const int want = 2 * ctx->sm_count;
@@ -489,7 +538,7 @@ static mh_status launch_tc(mh_ctx* ctx, const float4* d_pts, int64_t N, const fl
   unsigned grid_x = tiles;
   const int slots = MINB * ctx->sm_count;
   static const bool tail_on = !(std::getenv("MH_TAIL_SPLIT") && std::atoi(std::getenv("MH_TAIL_SPLIT")) == 0);   // measurement aid
-  if (tail_on && ks == 1 && (int)tiles > slots && tiles % slots != 0) {
+  if (tail_on && !LIST && ks == 1 && (int)tiles > slots && tiles % slots != 0) {
     const int tail = (int)(tiles % slots);
     double best_t = 1.0;
     for (int sp = 2; sp <= 16 && sp * CH <= K; sp *= 2) {
@@ -514,8 +563,8 @@ static mh_status launch_tc(mh_ctx* ctx, const float4* d_pts, int64_t N, const fl
   split_hyp_tf32_kernel<<<(unsigned)((Kpad + 127) / 128), 128, 0, ctx->stream>>>(d_hyp, K, Kpad, (float4*)d_split, d_wild_count,
                                                                                 d_wild_list);
   MH_LAUNCHED(ctx, "split_hyp_tf32_kernel");
-  const size_t smem = 2 * (size_t)CH * 96 + 2 * (size_t)WARPS * CH + 16 + (QTHR > 0 ? (size_t)WARPS * (queue_capacity(PB) + 16 * PB) * 4 : 0);
-  auto kern = cost_argmin_tc_kernel<COUNT_INLIERS, WARPS, MINB, PB, CH, PIPE, QTHR>;
+  const size_t smem = 2 * (size_t)CH * 96 + 2 * (size_t)WARPS * CH + 16 + (QTHR > 0 ? (size_t)WARPS * (queue_capacity(PB) + 16 * PB * (LIST ? 2 : 1)) * 4 : 0);
+  auto kern = cost_argmin_tc_kernel<COUNT_INLIERS, WARPS, MINB, PB, CH, PIPE, QTHR, LIST>;
   MH_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<dim3(grid_x, (unsigned)ks), WARPS * 32, smem, ctx->stream>>>(d_pts, N, d_hyp, d_split, K, kpb, cp, fo, ks > 1, tiles_full, tail_split,
                                                                       kpb_tail);
@@ -524,6 +573,13 @@ static mh_status launch_tc(mh_ctx* ctx, const float4* d_pts, int64_t N, const fl
   cost_argmin_wild_kernel<<<wild_grid, 256, 0, ctx->stream>>>(d_pts, N, d_hyp, d_wild_count, d_wild_list, cp, fo);
   MH_LAUNCHED(ctx, "cost_argmin_wild_kernel");
   return MH_OK;
+}
+
+// the list-producing member (mh_data_cost_fused with d_list): config 55's shape with the append-drain
+mh_status launch_cost_list_tc(mh_ctx* ctx, const float4* d_pts, int64_t N, const float* d_hyp, int K, const CostParams& cp,
+                              const FastOut& fo) {
+  return fo.inlier_count ? launch_tc<true, 4, 5, 3, 128, false, 32, true>(ctx, d_pts, N, d_hyp, K, cp, fo)
+                         : launch_tc<false, 4, 5, 3, 128, false, 32, true>(ctx, d_pts, N, d_hyp, K, cp, fo);
 }
 
 // config = 30 + i, see the table; returns MH_EINVAL for an unknown config

@@ -796,9 +796,12 @@ __global__ void fused_init_kernel(long long N, int K, int32_t* list_count, u64* 
 
 mh_status launch_cost_argmin_tc(mh_ctx* ctx, const float4* d_pts, int64_t N, const float* d_hyp, int K, const CostParams& cp,
                                 const FastOut& fo, int config);  // k2_mma.cu
+mh_status launch_cost_list_tc(mh_ctx* ctx, const float4* d_pts, int64_t N, const float* d_hyp, int K, const CostParams& cp,
+                              const FastOut& fo);  // k2_mma.cu
 mh_status launch_cost_argmin_tmem(mh_ctx* ctx, const float4* d_pts, int64_t N, const float* d_hyp, int K, const CostParams& cp,
                                   const FastOut& fo, int config);  // k2_tmem.cu
 
+int g_list_variant = 1;   // 1 = tensor-core list kernel (default), 0 = first-generation cost_fused_kernel
 int g_fused_variant = 1;  // 1 = packed FFMA2 (default), 0 = scalar FFMA (A/B evidence)
 int g_fast_config = 55;   // fast-path variant, see launch_cost_fused / launch_cost_argmin_tc; 55 = v7 tensor-core kernel, 4 warps x 5 CTAs/SM x 48 rows/warp (default); 5 = v3 FFMA2 kernel
 
@@ -825,6 +828,13 @@ mh_status launch_cost_fused(mh_ctx* ctx, const float4* d_pts, int64_t N, const f
   k_per_block = (k_per_block + 1) & ~1;  // even, so label pairs stay aligned
   ksplit = (K + k_per_block - 1) / k_per_block;
   dim3 grid(tiles, (unsigned)ksplit);
+  if (d_list && d_list_count && kmax > 0 && g_fused_variant == 1 && g_list_variant == 1 && K < 65535 && cp.cost_outlier <= 0xffff) {
+    // sparse lists from the tensor-core kernel (filter + deferred queue + append-drain); g_list_variant 0 = the first-generation
+    // emit-on-every-hit kernel below (cross-check)
+    FastOut fo{(u64*)d_best, d_inlier_count, d_list, d_list_count, kmax};
+    if (!d_best) return fail(ctx, MH_EINVAL, "mh_data_cost_fused: the list kernel also produces the argmin: pass d_best");
+    return launch_cost_list_tc(ctx, d_pts, N, d_hyp, K, cp, fo);
+  }
   if (!d_list && !d_list_count && g_fused_variant == 1) {
     FastOut fo{(u64*)d_best, d_inlier_count};
     const bool cnt = d_inlier_count != nullptr;
