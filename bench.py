@@ -288,39 +288,50 @@ def main():
         step_no[0] += 1
         ctx.step_sharded(b["pts"], b["aff"], d_hyp, b["hyp_pt"], b["best"], b["labels"], fused["inliers"], d_ref, events=ev)
 
-    def stats_and_refit():
-        """e2e ordering (K2 before K1): labels -> K4 statistics -> all-reduce -> solves, in stream order"""
-        ctx.labels_from_best(fused["best"], labels)                                          # -1 = outlier
-        d_ref.copy_(d_hyp)
-        ctx.refit_haf_accumulate(d_pts, d_aff, labels, K_HYP, out=acc)                       # K4 statistics
-        if world > 1:
-            ctx.pack_inlier_counts(fused["inliers"], acc)
-            ctx.comm_allreduce_sum_f64(acc)
-            ctx.pack_inlier_counts(fused["inliers"], acc, unpack=True)
-        ctx.refit_haf_solve(acc, d_ref)                                                      # K4 solves
-
-    # end-to-end: the two host->device uploads run on their own stream (second context = second stream, same geometry);
-    # K2 needs only the points, so it starts as soon as they have landed and hides the upload of the affines.
-    s_up = torch.cuda.Stream(device=dev)
+    # end-to-end: the host->device uploads run on their own stream (second context = second stream, same geometry), the
+    # device->host downloads on a third.
+    s_up = torch.cuda.Stream(device=dev, priority=-1)   # high priority: the small normalisation kernels must not queue behind K2
     ctx_up = m.Context(device=local, use_torch_stream=False)
     ctx_up.use_stream(s_up)
     ctx_up.set_geometry(sc.F, sc.pts)
-    ev_pts, ev_aff = torch.cuda.Event(), torch.cuda.Event()
+    # Consecutive e2e steps are pipelined, not serialised: step i+1's uploads (own stream) run under step i's kernels, every step
+    # still copies ITS inputs host->device and ITS results device->host inside the timed region; the buffer sets of the rotation
+    # double-buffer the device side, events hand them back to the upload stream, the host only synchronises at the end.
+    ev_done = [torch.cuda.Event() for _ in range(n_sets)]
+    h_labels2 = [h_labels, torch.empty_like(h_labels).pin_memory()]
+    h_ref2 = [h_ref, torch.empty_like(h_ref).pin_memory()]
+    e2e_no = [0]
+
+    s_down = torch.cuda.Stream(device=dev)
+    _dbg = os.environ.get("MH_E2E_DEBUG", "")   # measurement aid: "noup" / "nodown" drop the copies (the line is then not an e2e number)
+    ev_in = [torch.cuda.Event() for _ in range(n_sets)]
+    ev_res = torch.cuda.Event()
+    for b_ in sets:
+        b_["ref"] = torch.empty_like(d_ref)
+    last_done = [None]
 
     def e2e_pass():
+        """uploads (own stream) -> the same mh_step_sharded call the device-resident pass makes -> downloads (own stream)"""
+        i = e2e_no[0]; e2e_no[0] += 1
+        j = i % n_sets
+        b = sets[j]
         main = torch.cuda.current_stream()
-        ctx_up.upload(h_pts, None, out=(d_pts, None)); ev_pts.record(s_up)                  # H2D + normalise (points)
-        ctx_up.upload(None, h_aff, out=(None, d_aff)); ev_aff.record(s_up)                  # H2D + normalise (affines)
-        if world > 1:
-            ctx.comm_broadcast(d_hyp, root=0)
-        main.wait_event(ev_pts)
-        ctx.data_cost_fused(d_pts, d_hyp, kmax=0, want_list=False, out=fused)                # K2
-        main.wait_event(ev_aff)
-        ctx.haf_hypotheses(d_pts, d_aff, out=d_hyp_pt)                                      # K1
-        stats_and_refit()                                                                    # K4 (+ all-reduce)
-        h_labels.copy_(labels, non_blocking=True)                                            # D2H results
-        h_ref.copy_(d_ref, non_blocking=True)
-        torch.cuda.synchronize()
+        s_up.wait_event(ev_done[j])                                                          # the set's previous pass is done with it
+        if "noup" not in _dbg:
+            ctx_up.upload(h_pts, None, out=(b["pts"], None))                                # H2D + normalise (points)
+            ctx_up.upload(None, h_aff, out=(None, b["aff"]))                                # H2D + normalise (affines)
+        ev_in[j].record(s_up)
+        main.wait_event(ev_in[j])
+        ctx.step_sharded(b["pts"], b["aff"], d_hyp, b["hyp_pt"], b["best"], b["labels"], fused["inliers"], b["ref"])
+        ctx.step_sharded_finish()                                                            # this step's all-reduce + solves
+        ev_res.record(main)
+        s_down.wait_event(ev_res)
+        with torch.cuda.stream(s_down):
+            if "nodown" not in _dbg:
+                h_labels2[i & 1].copy_(b["labels"], non_blocking=True)                       # D2H results
+                h_ref2[i & 1].copy_(b["ref"], non_blocking=True)
+        ev_done[j].record(s_down)
+        last_done[0] = ev_done[j]
 
     def barrier():
         if world > 1:
@@ -373,6 +384,7 @@ def main():
     e0.record()
     for _ in range(args.steps):
         e2e_pass()
+    torch.cuda.current_stream().wait_event(last_done[0])   # the last step's downloads belong to the timed region
     e1.record()
     barrier()
     te = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
