@@ -931,3 +931,46 @@ def test_k2_tcgen05_variant_is_bit_exact(mh, config):
             assert torch.equal(f2["best"], f["best"])
     finally:
         ctx.set_fast_config(55)
+
+
+def test_k2_list_kernel_counts_and_lists_with_wild_hypotheses(mh):
+    """The tensor-core list member (mh_data_cost_fused with d_list): per-site entry counts and (sorted) lists equal the dense
+    matrix exactly — also for "wild" hypotheses (kept off the tensor cores, listed by the FP32 side pass; a wild hypothesis whose
+    pair partner raises the flag must not be listed twice) and when the hypothesis range is split over CTAs."""
+    import torch
+
+    sc = mh.scenes.make_scene(1 << 16, 20, seed=0xB200 + 3)
+    ctx = mh.Context()
+    ctx.set_geometry(sc.F, sc.pts)
+    d_pts, d_aff = ctx.upload(sc.pts, sc.aff)
+    d_h = ctx.haf_hypotheses(d_pts, d_aff)
+    idx = torch.randint(0, 1 << 16, (235,), device="cuda", generator=torch.Generator("cuda").manual_seed(4))
+    hyp = torch.cat([ctx.hypotheses_from_host(sc.planes), d_h[idx]]).contiguous()          # K = 255
+    # a wild hypothesis (the HAF estimate of some correspondence c: |h_i| > 4 |h33|) next to a tame pair partner that also fits c
+    # exactly (the pixel translation x1 -> x2 of c): on row c the partner raises the pair's flag, so the exact re-evaluation sees the
+    # wild hypothesis too — it must still be listed once (by the side pass), not twice
+    h9 = d_h[:, :9]
+    wild_rows = (~(h9[:, :8].abs().max(1).values <= 4 * h9[:, 8].abs())).nonzero().flatten()
+    assert len(wild_rows) >= 1
+    c = int(wild_rows[wild_rows < 2500][0]) if bool((wild_rows < 2500).any()) else int(wild_rows[0])
+    tx, ty = sc.pts[c, 2] - sc.pts[c, 0], sc.pts[c, 3] - sc.pts[c, 1]
+    hyp[2] = ctx.hypotheses_from_host(np.array([[1, 0, tx, 0, 1, ty, 0, 0, 1]], dtype=np.float64))[0]
+    hyp[3] = d_h[c]
+    h9 = hyp[:, :9]
+    assert not bool(h9[2, :8].abs().max() > 4 * h9[2, 8].abs()) and bool(h9[3, :8].abs().max() > 4 * h9[3, 8].abs())
+    kmax = 64
+    for pts in (d_pts, d_pts[:2500].contiguous()):
+        dense = ctx.data_cost_dense(pts, hyp)
+        f = ctx.data_cost_fused(pts, hyp, kmax=kmax)
+        cnt_d = (dense[:, 1:] <= 255).sum(1).int()
+        assert torch.equal(f["count"], cnt_d)
+        assert torch.equal(f["best"] & 0xFFFFFFFF, dense.argmin(1)) and torch.equal(f["best"] >> 32, dense.min(1).values.to(torch.int64))
+        lab = torch.arange(1, dense.shape[1], device="cuda", dtype=torch.int64)[None, :].expand(dense.shape[0], -1)
+        exp = torch.where(dense[:, 1:] <= 255, (lab << 8) | dense[:, 1:].to(torch.int64), torch.full_like(lab, 1 << 40))
+        exp = torch.sort(exp, 1).values[:, :kmax]
+        got = f["list"].to(torch.int64).masked_fill(torch.arange(kmax, device="cuda")[None, :] >= f["count"][:, None], 1 << 40)
+        got = torch.sort(got, 1).values
+        fit = cnt_d <= kmax
+        assert bool(fit.any()) and torch.equal(got[fit], exp[fit])
+        if c < pts.shape[0]:
+            assert int(dense[c, 3]) <= 255 and int(dense[c, 4]) <= 255      # row c really holds both entries of the pair
