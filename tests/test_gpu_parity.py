@@ -974,3 +974,32 @@ def test_k2_list_kernel_counts_and_lists_with_wild_hypotheses(mh):
         assert bool(fit.any()) and torch.equal(got[fit], exp[fit])
         if c < pts.shape[0]:
             assert int(dense[c, 3]) <= 255 and int(dense[c, 4]) <= 255      # row c really holds both entries of the pair
+
+
+def test_pipeline_20k_correspondences_vs_oracle_pipeline(mh, orc):
+    """A scene of 20 000 correspondences (8 planes) through mh_process vs the oracle pipeline: same clusters, same labels.
+    At this size the reference's own GCO needs minutes per labelling step, so the oracle pipeline's max-flow is the library's
+    host expansion — which tests/test_host.py proves bit-identical to the reference GCO on four problem families — and the
+    claim is re-checked here on this scene's own FIRST labelling problem (cold start, most labels) against the reference GCO."""
+    from ref_pipeline import oracle_process
+
+    sc = mh.scenes.make_scene(20000, 8, seed=0xB200 + 41)
+    problems = []
+
+    def expansion(cost, off, adj, init):
+        lab, e = mh.capi.alpha_expansion(cost, 50, off, adj, init)
+        if not problems:
+            problems.append((cost.copy(), off.copy(), adj.copy(), None if init is None else init.copy(), lab.copy(), e))
+        return e, lab
+
+    assert orc.smooth_cost(0, 1, 0.5) == 50
+    lab_o, H_o, info = oracle_process(sc.pts, sc.aff, sc.F, compatibility_check=True, lm=True, expansion=expansion)
+    lab, H, K = mh.Context().process(sc.pts, sc.aff, sc.F)
+    print(f"\n[parity] 20k scene: K gpu={K} oracle={len(H_o)} agreement={(lab == lab_o).mean():.5f} outliers={(lab < 0).mean():.3f} "
+          f"iterations={info['iterations']}")
+    assert K == len(H_o) and np.array_equal(lab, lab_o)
+    assert np.abs(H / H[:, 8:9] - H_o / H_o[:, 8:9]).max() <= 1e-6
+    if orc.ref_lib() is not None and problems[0][0].shape[1] <= 64:      # the reference GCO on the scene's first labelling problem
+        cost, off, adj, init, lab_l, e_l = problems[0]
+        e_r, lab_r = orc.gco_ref_expansion(cost, 50, off, adj, init, 1000)
+        assert e_r == e_l and np.array_equal(lab_r, lab_l)
