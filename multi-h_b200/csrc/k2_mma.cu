@@ -528,6 +528,7 @@ static mh_status launch_tc(mh_ctx* ctx, const float4* d_pts, int64_t N, const fl
   const unsigned tiles = (unsigned)((N + tile - 1) / tile);
   int ks = 1;
   if ((int)tiles < want) ks = std::min((K + CH - 1) / CH, (want + (int)tiles - 1) / (int)tiles);
+  if (const char* e = std::getenv("MH_K2_KSPLIT")) ks = std::min((K + CH - 1) / CH, std::max(1, std::atoi(e)));   // measurement aid
   ks = std::max(1, ks);
   int kpb = (K + ks - 1) / ks;
   kpb = ((kpb + CH - 1) / CH) * CH;   // whole chunks per CTA

@@ -17,11 +17,14 @@
 //      trajectories over sparse windows are speculated (<= MS_CAP_A windows of <=
 //      MS_RANGE_A candidates): those are the many isolated points; the few seeds inside
 //      dense clusters drift for dozens of windows, and nearly all of their neighbours are
-//      visited before they could ever be drawn — speculating them would cost more than
-//      the whole sequential algorithm.
+//      visited before they could ever be drawn.
+//   A2. ms_heavy_kernel (N >= MS_HEAVY_MIN_N) — the seeds step A leaves out, chip-wide, one CTA per seed, with the same block-wide
+//      trajectory code the replay uses; votes go to a heavy record (one byte per sorted position of a MS_HSPAN-wide span).
+//      Measured at 20 000 points: 307 of 1779 drawn seeds were such trajectories and cost the one replay CTA 88 % of its
+//      time (93 us each); computing all ~10^4 candidates on 148 SMs takes 5 ms and the call drops from 33.5 to 14.0 ms.
 //   B. ms_replay_kernel — one CTA replays the reference's sequential part exactly: the
 //      restated MSVC rand() picks the rank-th unvisited point in index order (MS.h:54-56);
-//      its trajectory comes from step A's record or is computed on the spot by the whole
+//      its trajectory comes from step A's / A2's record or is computed on the spot by the whole
 //      CTA; the windows mark their members visited and give them their votes (MS.h:85-93);
 //      the final mean is merged into the first centre closer than bw/2 or appended
 //      (MS.h:100-120); per-point votes live in sparse (cluster, votes) lists and the last
@@ -57,6 +60,10 @@ constexpr int MS_RANGE_A = 1024;        // ... each with at most this many candi
 constexpr int MS_SMEM_MASK_WORDS = 32768;  // visited bits of up to 2^20 points live in shared memory (step B)
 constexpr int MS_SORT_SMALL_MAX = 4096;    // up to here one CTA sorts in shared memory; beyond: cub radix sort
 constexpr int MS_BRUTE_CENTRES = 1024;     // merge test: scan all centres up to here, cell hash beyond
+constexpr int MS_HSPAN = 16384;            // widest union of candidate ranges a heavy record holds (one byte per sorted position)
+constexpr int MS_HHDR = MS_MAXD + 4;       // doubles per heavy record header
+constexpr int MS_HEAVY_MIN_N = 8192;       // below this the replay CTA computes the few heavy trajectories itself
+constexpr int MS_HEAVY_MAX_SLOTS = 32768;  // 512 MB of vote bytes at most
 constexpr int MS_HASH_DIMS = 3;
 constexpr int MS_STAGE1 = 3;               // coordinates summed before the first early exit of the window test
 
@@ -72,6 +79,12 @@ struct MsProblem {
   // ---- speculated trajectories by ORIGINAL index (step A -> step B) ----
   double* rec;         // [N][rec_stride], layout at ms_rec_stride()
   int rec_stride;
+  // ---- heavy trajectories (step A2 -> step B): the seeds step A leaves out, one CTA each, chip-wide; nullptr below MS_HEAVY_MIN_N
+  int32_t* heavy_list;        // [heavy_cap] sorted positions, in the order step A found them
+  int32_t* heavy_slot;        // [N] by original index: slot in the heavy pool, -1 = none
+  double* heavy_hdr;          // [heavy_cap][MS_HHDR]: n | final mean | (ulo, uhi) | vbase
+  unsigned char* heavy_votes; // [heavy_cap][MS_HSPAN] windows per sorted position, relative to vbase
+  int heavy_cap;
   // ---- step B state ----
   int32_t* tvotes;     // [Npad] by sorted position: votes of the running on-the-spot trajectory
   int32_t* vl_n;       // [N]
@@ -91,7 +104,7 @@ struct MsProblem {
   double* centres;     // [max_c][D]
   int max_c;
   int32_t* assign;     // [N]
-  // ctl: [0] C  [1] flags  [2] n_finite  [3] spill_used  [4] trajectories computed on the spot  [6,7] trajectories (u64)
+  // ctl: [0] C  [1] flags  [2] n_finite  [3] spill_used  [4] trajectories computed on the spot  [5] heavy seeds  [6,7] trajectories (u64)
   //      [8,9] window iterations (u64)  [10] rng state
   int32_t* ctl;
 };
@@ -387,6 +400,14 @@ __global__ void __launch_bounds__(MS_TRAJ_THREADS) ms_trajectories_kernel(MsProb
       if (lane == j + 1) v = mean[j];
     if (lane == D + 1) v = __hiloint2double(uhi, ulo);
     if (lane <= D + 1) blk[lane] = v;
+    if (p.heavy_slot && lane == 0) {   // not speculated here: a CTA of step A2 takes it
+      int slot = -1;
+      if (n < 0) {
+        const int sl = atomicAdd(p.ctl + 5, 1);
+        if (sl < p.heavy_cap) { slot = sl; p.heavy_list[sl] = pos; }
+      }
+      p.heavy_slot[p.perm[pos]] = slot;
+    }
     if (n > 0) {
       // at least the part step B fetches unconditionally is written whole, so that the fetch finds its lines in L2
       uint32_t* out = reinterpret_cast<uint32_t*>(blk + D + 2);
@@ -450,8 +471,9 @@ struct MsShared {   // fixed part of step B's shared memory
 // One trajectory computed by the whole CTA, for a seed step A did not speculate (dense neighbourhood or slow drift): every window
 // scans its candidate range with all threads and leaves one vote per member in tvotes (by sorted position).  sh.cur holds
 // the seed on entry and the final mean on exit.  Returns the number of windows; [ulo, uhi) = union of the candidate ranges.
-template <int DT>
-__device__ __forceinline__ int ms_block_trajectory(const MsProblem& p, const MsRows& r, int32_t* tvotes, MsShared& sh, int Nf,
+// `votes`: begin(it, lo, hi) -> false abandons the trajectory (returns -1; CTA-uniform), add(q) records one window for position q.
+template <int DT, class SH, class Votes>
+__device__ __forceinline__ int ms_block_trajectory(const MsProblem& p, const MsRows& r, Votes& votes, SH& sh, int Nf,
                                                    int& ulo, int& uhi) {
   constexpr int T = MS_REPLAY_THREADS;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, D = p.D;
@@ -463,6 +485,7 @@ __device__ __forceinline__ int ms_block_trajectory(const MsProblem& p, const MsR
 #pragma unroll
     for (int j = 0; j < DT; ++j) mean[j] = j < D ? sh.cur[j] : 0.0;
     ms_range(r.xs, Nf, mean[0], p.bandSq, p.metric, lane, lo, hi, it > 0);   // every warp finds the same range
+    if (!votes.begin(it, lo, hi)) return -1;
     ulo = min(ulo, lo);
     uhi = max(uhi, hi);
     double acc[DT];
@@ -477,7 +500,7 @@ __device__ __forceinline__ int ms_block_trajectory(const MsProblem& p, const MsR
           for (int j = 0; j < DT; ++j)
             if (j < D) acc[j] += x[j];
           ++cnt;
-          tvotes[q] += 1;   // one thread per position and window; windows are separated by barriers
+          votes.add(q);   // one thread per position and window; windows are separated by barriers
         }
       }
     };
@@ -513,6 +536,56 @@ __device__ __forceinline__ int ms_block_trajectory(const MsProblem& p, const MsR
     if (sh.stop) break;
   }
   return it;
+}
+
+struct MsVotesInPlace {   // the on-the-spot trajectory of step B: votes by sorted position in global memory, consumed right away
+  int32_t* tvotes;
+  __device__ __forceinline__ bool begin(int, int, int) { return true; }
+  __device__ __forceinline__ void add(int q) { tvotes[q] += 1; }
+};
+struct MsVotesHeavy {     // step A2: one byte per position of a fixed span around the first window
+  unsigned char* bytes;
+  int vbase;
+  __device__ __forceinline__ bool begin(int it, int lo, int hi) {
+    if (it == 0) vbase = max(0, lo - (MS_HSPAN - min(hi - lo, MS_HSPAN)) / 2);   // room to drift either way
+    return lo >= vbase && hi <= vbase + MS_HSPAN;
+  }
+  __device__ __forceinline__ void add(int q) { bytes[q - vbase] += 1; }   // <= MH_MS_MAX_WINDOW_ITERS (200) windows: fits a byte
+};
+struct MsHeavyShared {
+  double cur[MS_MAXD];
+  double red[MS_REPLAY_WARPS][MS_MAXD + 1];
+  int redc[MS_REPLAY_WARPS];
+  int stop;
+};
+
+// ---- step A2: the trajectories step A did not speculate (dense neighbourhoods, slow drifts), one CTA per seed, all SMs -------
+// Same code as the replay's on-the-spot trajectory; the windows' votes go to the seed's heavy record.  A trajectory whose windows
+// leave the record's span is abandoned (n = -1) and computed by the replay if it ever draws that seed.
+template <int DT>
+__global__ void __launch_bounds__(MS_REPLAY_THREADS) ms_heavy_kernel(MsProblem p) {
+  __shared__ MsHeavyShared sh;
+  const int tid = threadIdx.x, D = p.D, Nf = p.ctl[2];
+  const int nh = min(p.ctl[5], p.heavy_cap);
+  const MsRows rows{p.xs, (size_t)p.Npad, p.perm};
+  for (int slot = blockIdx.x; slot < nh; slot += gridDim.x) {
+    const int pos = p.heavy_list[slot];
+    unsigned char* bytes = p.heavy_votes + (size_t)slot * MS_HSPAN;
+    for (int i = tid; i < MS_HSPAN / 16; i += MS_REPLAY_THREADS) reinterpret_cast<uint4*>(bytes)[i] = make_uint4(0, 0, 0, 0);
+    if (tid < D) sh.cur[tid] = p.xs[(size_t)tid * p.Npad + pos];
+    __syncthreads();
+    MsVotesHeavy votes{bytes, 0};
+    int ulo, uhi;
+    const int n = ms_block_trajectory<DT>(p, rows, votes, sh, Nf, ulo, uhi);
+    double* hdr = p.heavy_hdr + (size_t)slot * MS_HHDR;
+    if (tid == 0) {
+      hdr[0] = (double)n;
+      hdr[D + 1] = __hiloint2double(uhi, ulo);
+      hdr[D + 2] = (double)votes.vbase;
+    }
+    if (n > 0 && tid < D) hdr[1 + tid] = sh.cur[tid];
+    __syncthreads();   // sh.cur is rewritten by the next seed
+  }
 }
 
 struct MsVoteList {   // a point's (cluster, votes) list header, fetched ahead of its update
@@ -677,10 +750,29 @@ __global__ void __launch_bounds__(MS_REPLAY_THREADS, 1) ms_replay_kernel(MsProbl
     int n = (int)sh.rec[0];
     const bool speculated = n > 0;
     int ulo = __double2loint(sh.rec[D + 1]), uhi = __double2hiint(sh.rec[D + 1]);
-    if (!speculated) {
-      n = ms_block_trajectory<DT>(p, rows, tvotes, sh, Nf, ulo, uhi);
+    const unsigned char* hvotes = nullptr;   // a heavy record of step A2: vote bytes in global memory, relative to hbase
+    int hbase = 0;
+    if (!speculated && p.heavy_slot) {
+      const int slot = p.heavy_slot[seed];
+      if (slot >= 0) {
+        const double* hdr = p.heavy_hdr + (size_t)slot * MS_HHDR;
+        const int nh = (int)hdr[0];
+        if (nh > 0) {
+          n = nh;
+          const double ur = hdr[D + 1];
+          ulo = __double2loint(ur); uhi = __double2hiint(ur);
+          hbase = (int)hdr[D + 2];
+          hvotes = p.heavy_votes + (size_t)slot * MS_HSPAN;
+          if (tid < D) sh.cur[tid] = hdr[1 + tid];   // the final mean
+          __syncthreads();
+        }
+      }
+    }
+    if (!speculated && !hvotes) {
+      MsVotesInPlace inplace{tvotes};
+      n = ms_block_trajectory<DT>(p, rows, inplace, sh, Nf, ulo, uhi);
       ++on_the_spot;
-    } else if (uhi - ulo > MS_VOTE_SHORT) {   // a wide trajectory: the rest of its vote bytes
+    } else if (speculated && uhi - ulo > MS_VOTE_SHORT) {   // a wide trajectory: the rest of its vote bytes
       for (int i = ms_rec_short(D) + tid; i < D + 2 + (uhi - ulo + 7) / 8; i += T) sh.rec[i] = p.rec[(size_t)seed * p.rec_stride + i];
       __syncthreads();
     }
@@ -693,6 +785,7 @@ __global__ void __launch_bounds__(MS_REPLAY_THREADS, 1) ms_replay_kernel(MsProbl
     // votes of position q: as recorded by step A, or as left behind by the on-the-spot trajectory
     auto votes_of = [&](int q) {
       if (speculated) return (int)rvotes[q - ulo];
+      if (hvotes) return (int)hvotes[q - hbase];
       const int v = tvotes[q];
       if (v) tvotes[q] = 0;
       return v;
@@ -865,6 +958,10 @@ static mh_status launch_ms_kernels(mh_ctx* ctx, const MsProblem& p, size_t repla
   MH_CUDA(ctx, mh_allow_max_smem(ms_trajectories_kernel<DT>));
   ms_trajectories_kernel<DT><<<blocks, MS_TRAJ_THREADS, traj_smem, ctx->stream>>>(p);
   MH_LAUNCHED(ctx, "ms_trajectories_kernel");
+  if (p.heavy_slot) {
+    ms_heavy_kernel<DT><<<ctx->sm_count * 4, MS_REPLAY_THREADS, 0, ctx->stream>>>(p);
+    MH_LAUNCHED(ctx, "ms_heavy_kernel");
+  }
   auto kern = mode == 0 ? ms_replay_kernel<DT, 0> : mode == 1 ? ms_replay_kernel<DT, 1> : ms_replay_kernel<DT, 2>;
   MH_CUDA(ctx, mh_allow_max_smem(kern));
   kern<<<1, MS_REPLAY_THREADS, replay_smem, ctx->stream>>>(p);
@@ -904,6 +1001,11 @@ mh_status launch_meanshift(mh_ctx* ctx, const double* d_feat, int N, int D, doub
     const uint64_t o_gcnt1 = take(mask_words > MS_SMEM_MASK_WORDS ? sizeof(int32_t) * (uint64_t)(mask_words >> 5) : 0);
     const int rec_stride = ms_rec_stride(D);
     const uint64_t o_rec = take(sizeof(double) * (uint64_t)N * rec_stride);
+    const int heavy_cap = (N >= MS_HEAVY_MIN_N && metric != 2) ? std::min(N, MS_HEAVY_MAX_SLOTS) : 0;
+    const uint64_t o_hlist = take(sizeof(int32_t) * (uint64_t)heavy_cap);
+    const uint64_t o_hslot = take(heavy_cap ? sizeof(int32_t) * (uint64_t)N : 0);
+    const uint64_t o_hhdr = take(sizeof(double) * (uint64_t)heavy_cap * MS_HHDR);
+    const uint64_t o_hvotes = take((uint64_t)heavy_cap * MS_HSPAN);
     const uint64_t o_tv = take(sizeof(int32_t) * (uint64_t)Npad);
     const uint64_t o_vn = take(sizeof(int32_t) * (uint64_t)N);
     const uint64_t o_vid = take(sizeof(int32_t) * (uint64_t)N * MS_VCAP);
@@ -932,6 +1034,11 @@ mh_status launch_meanshift(mh_ctx* ctx, const double* d_feat, int N, int D, doub
     p.metric = metric;
     p.rec = (double*)(base + o_rec);
     p.rec_stride = rec_stride;
+    p.heavy_cap = heavy_cap;
+    p.heavy_list = heavy_cap ? (int32_t*)(base + o_hlist) : nullptr;
+    p.heavy_slot = heavy_cap ? (int32_t*)(base + o_hslot) : nullptr;
+    p.heavy_hdr = heavy_cap ? (double*)(base + o_hhdr) : nullptr;
+    p.heavy_votes = heavy_cap ? (unsigned char*)(base + o_hvotes) : nullptr;
     p.tvotes = (int32_t*)(base + o_tv);
     p.vl_n = (int32_t*)(base + o_vn);
     p.vl_id = (int32_t*)(base + o_vid);

@@ -368,8 +368,9 @@ def test_k3_meanshift_gram_tensor_core_variant(mh, orc):
 
 
 def test_k3_meanshift_cooperative_path_vs_oracle(mh, orc):
-    """N > 8192 takes the persistent cooperative kernel (chip-wide passes, grid barriers); N <= 8192 above takes the one-CTA
-    variant.  Same statement for both: the oracle's trajectories, window iterations and centres."""
+    """N >= 8192 adds step A2 (ms_heavy_kernel: the trajectories step A does not speculate — dense neighbourhoods — computed
+    chip-wide, one CTA per seed, and replayed from their heavy records); below it the replay CTA computes those few itself.
+    Same statement for both: the oracle's trajectories, window iterations, centres and assignments."""
     import torch
 
     sc = mh.scenes.make_scene(9000, 6, seed=11)
@@ -380,6 +381,7 @@ def test_k3_meanshift_cooperative_path_vs_oracle(mh, orc):
     assert st == sto and cen.shape[0] == co.shape[0]
     assert np.abs(cen.cpu().numpy() - co).max() <= 1e-6
     assert (asg.cpu().numpy() == ao).mean() >= 0.999
+    assert ctx.launches > 0
 
 
 def test_k3_meanshift_cycling_trajectory_is_capped_like_the_oracle(mh, orc):
