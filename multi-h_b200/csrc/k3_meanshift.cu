@@ -62,7 +62,7 @@ constexpr int MS_SORT_SMALL_MAX = 4096;    // up to here one CTA sorts in shared
 constexpr int MS_BRUTE_CENTRES = 1024;     // merge test: scan all centres up to here, cell hash beyond
 constexpr int MS_HSPAN = 16384;            // widest union of candidate ranges a heavy record holds (one byte per sorted position)
 constexpr int MS_HHDR = MS_MAXD + 4;       // doubles per heavy record header
-constexpr int MS_HEAVY_MIN_N = 8192;       // below this the replay CTA computes the few heavy trajectories itself
+constexpr int MS_HEAVY_MIN_N = 2048;       // below this the replay CTA computes the few heavy trajectories itself
 constexpr int MS_HEAVY_MAX_SLOTS = 32768;  // 512 MB of vote bytes at most
 constexpr int MS_HASH_DIMS = 3;
 constexpr int MS_STAGE1 = 3;               // coordinates summed before the first early exit of the window test

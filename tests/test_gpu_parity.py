@@ -368,7 +368,7 @@ def test_k3_meanshift_gram_tensor_core_variant(mh, orc):
 
 
 def test_k3_meanshift_cooperative_path_vs_oracle(mh, orc):
-    """N >= 8192 adds step A2 (ms_heavy_kernel: the trajectories step A does not speculate — dense neighbourhoods — computed
+    """N >= 2048 adds step A2 (ms_heavy_kernel: the trajectories step A does not speculate — dense neighbourhoods — computed
     chip-wide, one CTA per seed, and replayed from their heavy records); below it the replay CTA computes those few itself.
     Same statement for both: the oracle's trajectories, window iterations, centres and assignments."""
     import torch
