@@ -13,6 +13,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 import subprocess
+import sys
 
 import numpy as np
 
@@ -77,6 +78,24 @@ def ref_multih_lib():
     return _refmh
 
 
+class _StdoutToStderr:
+    """The reference source reports its progress with printf; keep the caller's stdout clean (bench.py prints ONE JSON line there)
+    by pointing file descriptor 1 at stderr while it runs."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self._saved = os.dup(1)
+        os.dup2(2, 1)
+
+    def __exit__(self, *exc):
+        try:
+            C.CDLL(None).fflush(None)
+        except Exception:
+            pass
+        os.dup2(self._saved, 1)
+        os.close(self._saved)
+
+
 def ref_process(pts, aff, F, thr_fund=2.6, thr=2.2, locality=0.005, lam=0.5, min_inliers=20, rng_state=1, lm=True):
     """MultiH::Process() of the reference source (MultiH.cpp:32-98) with F injected in place of its RANSAC, MSVC rand(), the exact
     31-nearest neighbourhood for FLANN, and its LM solver on (lm=True) or leaving the linear solutions untouched (lm=False).
@@ -85,10 +104,12 @@ def ref_process(pts, aff, F, thr_fund=2.6, thr=2.2, locality=0.005, lam=0.5, min
     N = len(pts)
     lab = np.full(N, -9, dtype=np.int32); H = np.zeros((4096, 9)); po = np.zeros((N, 4)); ho = np.zeros((N, 9))
     K, kept, it, dg, en = C.c_int(0), C.c_int(0), C.c_int(0), C.c_int(0), C.c_double(0)
-    rc = ref_multih_lib().ref_multih_process(pp, pa, pf, N, C.c_double(thr_fund), C.c_double(thr), C.c_double(locality), C.c_double(lam),
-                                              int(min_inliers), C.c_uint(rng_state), int(bool(lm)), lab.ctypes.data_as(c_ip),
-                                              H.ctypes.data_as(c_dp), 4096, C.byref(K), po.ctypes.data_as(c_dp),
-                                              ho.ctypes.data_as(c_dp), C.byref(kept), C.byref(it), C.byref(en), C.byref(dg))
+    with _StdoutToStderr():
+        rc = ref_multih_lib().ref_multih_process(pp, pa, pf, N, C.c_double(thr_fund), C.c_double(thr), C.c_double(locality),
+                                                  C.c_double(lam), int(min_inliers), C.c_uint(rng_state), int(bool(lm)),
+                                                  lab.ctypes.data_as(c_ip), H.ctypes.data_as(c_dp), 4096, C.byref(K),
+                                                  po.ctypes.data_as(c_dp), ho.ctypes.data_as(c_dp), C.byref(kept), C.byref(it),
+                                                  C.byref(en), C.byref(dg))
     if rc:
         raise RuntimeError("the reference's Process() refused the input (fewer than 8 correspondences)")
     M = kept.value
