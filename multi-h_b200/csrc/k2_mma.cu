@@ -259,25 +259,21 @@ cost_argmin_tc_kernel(const float4* __restrict__ pts, long long N, const float* 
     __syncwarp();
     for (int i = lane; i < qcnt; i += 32) {
       const unsigned e = sQ[i];
-      // LIST entries say which hypothesis of the pair raised the flag (bits 22, 23): only that one is re-evaluated
-      const int row = (int)(e >> 24), ih0 = (int)(e & (LIST ? 0x3fffffu : 0xffffffu));
-      const bool do_a = !LIST || ((e >> 22) & 1u), do_b = !LIST || ((e >> 23) & 1u);
+      const int row = (int)(e >> 24), ih0 = (int)(e & 0xffffffu);
       const float4 q = __ldg(pts + tile0 + row);   // < N: padding rows never raise a flag
       float ha[9], hb[9];
-#pragma unroll
-      for (int k = 0; k < 9; ++k) ha[k] = hb[k] = (k == 2 || k == 5) ? 1e18f : (k == 8 ? 1.f : 0.f);   // "far": d2 ~ 1e36
-      if (do_a) {
+      {
         const float4* hp = reinterpret_cast<const float4*>(hyp + (size_t)min(ih0, K - 1) * 12);
         const float4 u = __ldg(hp), v = __ldg(hp + 1), w = __ldg(hp + 2);
         ha[0] = u.x; ha[1] = u.y; ha[2] = u.z; ha[3] = u.w; ha[4] = v.x; ha[5] = v.y; ha[6] = v.z; ha[7] = v.w; ha[8] = w.x;
       }
-      if (do_b) {
+      {
         const float4* hp = reinterpret_cast<const float4*>(hyp + (size_t)min(ih0 + 1, K - 1) * 12);
         const float4 u = __ldg(hp), v = __ldg(hp + 1), w = __ldg(hp + 2);
         hb[0] = u.x; hb[1] = u.y; hb[2] = u.z; hb[3] = u.w; hb[4] = v.x; hb[5] = v.y; hb[6] = v.z; hb[7] = v.w; hb[8] = w.x;
       }
-      const float da = do_a ? residual(ha, q.x, q.y, q.z, q.w) : 3.0e38f;
-      const float db = do_b ? residual(hb, q.x, q.y, q.z, q.w) : 3.0e38f;
+      const float da = residual(ha, q.x, q.y, q.z, q.w);
+      const float db = residual(hb, q.x, q.y, q.z, q.w);
       unsigned mine = 0xffffffffu;
       if (ih0 < kend && da < cp.T) mine = ((unsigned)cost_in_range(da, cp) << 16) | (unsigned)(ih0 + 1);
       if (ih0 + 1 < kend && db < cp.T) mine = min(mine, ((unsigned)cost_in_range(db, cp) << 16) | (unsigned)(ih0 + 2));
@@ -321,7 +317,6 @@ cost_argmin_tc_kernel(const float4* __restrict__ pts, long long N, const float* 
   auto epilogue = [&](const Acc<PB>& a, int ih_block) -> unsigned {
     unsigned mask0 = 0u, mask1 = 0u;   // v6: shifted-in sign bits; DEFER: running counts (LEA.HI, no POPC)
     bool flag[PB][2];
-    unsigned sel[PB][2];   // LIST: which of the slot's two hypotheses is inside the interval
     bool any = false;
 #pragma unroll
     for (int pb = 0; pb < PB; ++pb)
@@ -346,13 +341,7 @@ cost_argmin_tc_kernel(const float4* __restrict__ pts, long long N, const float* 
         } else {
           upk(fma2(dx, dx, fma2(dy, dy, pk(CM[pb][r], CM[pb][r]))), ta, tb);   // d2 - mid
         }
-        if (LIST) {
-          sel[pb][r] = (fabsf(ta) < HALF[pb][r] ? 1u : 0u) | (fabsf(tb) < HALF[pb][r] ? 2u : 0u);
-          flag[pb][r] = sel[pb][r] != 0u;
-        } else {
-          sel[pb][r] = 0u;
-          flag[pb][r] = fminf(fabsf(ta), fabsf(tb)) < HALF[pb][r];
-        }
+        flag[pb][r] = fminf(fabsf(ta), fabsf(tb)) < HALF[pb][r];
         any = any || flag[pb][r];
       }
     if (__any_sync(0xffffffffu, any)) {   // rare after warm-up
@@ -366,8 +355,7 @@ cost_argmin_tc_kernel(const float4* __restrict__ pts, long long N, const float* 
             if (m) {
               const int n = __popc(m);
               if (flag[pb][r])
-                sQ[qcnt + __popc(m & ((1u << lane) - 1u))] =
-                    ((unsigned)(pb * 16 + g + 8 * r) << 24) | (sel[pb][r] << 22) | (unsigned)(ih_block + 2 * t);
+                sQ[qcnt + __popc(m & ((1u << lane) - 1u))] = ((unsigned)(pb * 16 + g + 8 * r) << 24) | (unsigned)(ih_block + 2 * t);
               qcnt += n;
             }
           } else if (__any_sync(0xffffffffu, flag[pb][r])) {
