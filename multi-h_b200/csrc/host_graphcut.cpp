@@ -35,8 +35,36 @@
 #include <vector>
 
 #include "../../include/multih_b200.h"
+#ifdef MH_GC_PROFILE
+#include <x86intrin.h>
+
+#include <cstdio>
+#endif
 
 namespace mh {
+
+#ifdef MH_GC_PROFILE   // make EXTRA=-DMH_GC_PROFILE: cycle counters per phase of the expansion, printed at exit (single-threaded runs)
+static unsigned long long g_prof[16];
+static unsigned long long g_prof_n[16];
+struct GcProfPrinter {
+  ~GcProfPrinter() {
+    static const char* names[] = {"candidate scan", "bounds init", "reduction", "network build", "max-flow", "tally", "memo checks",
+                                  "setup", "total", "commit", "", "", "", "", "", ""};
+    std::fprintf(stderr, "[gc profile] moves with candidates %llu: mean C0 %.1f, decided at once %.1f, network sites %.1f (non-empty networks %llu), sure switchers %.1f\n",
+                 g_prof_n[1], g_prof[10] / (double)g_prof_n[1], g_prof[11] / (double)g_prof_n[1], g_prof[12] / (double)g_prof_n[1], g_prof_n[12],
+                 g_prof[13] / (double)g_prof_n[1]);
+    for (int i = 0; i < 10; ++i)
+      std::fprintf(stderr, "[gc profile] %-16s %10.1f Mcycles  (%llu)  %5.1f %%\n", names[i], g_prof[i] / 1e6, g_prof_n[i],
+                   100.0 * g_prof[i] / (double)(g_prof[8] ? g_prof[8] : 1));
+  }
+};
+static GcProfPrinter g_prof_printer;
+#define GC_TICK(var) const unsigned long long var = __rdtsc()
+#define GC_ACC(slot, from) do { g_prof[slot] += __rdtsc() - (from); ++g_prof_n[slot]; } while (0)
+#else
+#define GC_TICK(var) do { } while (0)
+#define GC_ACC(slot, from) do { } while (0)
+#endif
 
 // ---------------------------------------------------------------------------
 // Dinic max-flow on a static arc array (paired arcs e, e^1).
@@ -355,6 +383,7 @@ static void eval_move(const MoveProblem& P, const int32_t* lab, int alpha, MoveW
   // sure switchers and lies inside S, so the reduced problem has the same minimisers and the same maximal one (the labelling
   // GCO returns).
   cand.clear();
+  GC_TICK(t_scan);
   {
     const int32_t* ca = P.costT + (size_t)alpha * N;
     const int32_t* cc = P.cur;
@@ -363,8 +392,10 @@ static void eval_move(const MoveProblem& P, const int32_t* lab, int alpha, MoveW
       if (((int64_t)ca[i] - cc[i] <= wa[i]) & (lab[i] != alpha)) cand.push_back(i);
     for (size_t a = 0; a < cand.size(); ++a) var[cand[a]] = (int)a;
   }
+  GC_ACC(0, t_scan);
   if (cand.empty()) return;
   r.any_c0 = true;
+  GC_TICK(t_init);
   const size_t n0 = cand.size();
   Wcur.resize(n0); Ucur.resize(n0); Dcur.resize(n0);
   std::vector<char>& st = ws.state;   // per initial candidate: 0 = undecided, 1 = queued/decided keep, 2 = queued/decided switch
@@ -390,6 +421,11 @@ static void eval_move(const MoveProblem& P, const int32_t* lab, int alpha, MoveW
     if (Dcur[a] > Wcur[a]) { st[a] = 1; work.push_back((int)a); }
     else if (Dcur[a] + Ucur[a] < 0) { st[a] = 2; work.push_back((int)a); }
   }
+  GC_ACC(1, t_init);
+#ifdef MH_GC_PROFILE
+  g_prof[10] += n0; g_prof[11] += work.size();
+#endif
+  GC_TICK(t_red);
   fsw.clear();
   for (size_t q = 0; q < work.size(); ++q) {
     const int a = work[q], i = cand[a];
@@ -418,6 +454,10 @@ static void eval_move(const MoveProblem& P, const int32_t* lab, int alpha, MoveW
     }
     cand.resize(keep);
   }
+  GC_ACC(2, t_red);
+#ifdef MH_GC_PROFILE
+  g_prof[12] += cand.size(); g_prof[13] += fsw.size(); g_prof_n[12] += !cand.empty();
+#endif
   if (cand.empty() && fsw.empty()) return;
   for (size_t a = 0; a < cand.size(); ++a) var[cand[a]] = (int)a;
   std::vector<int32_t>& trial = ws.trial;
@@ -426,6 +466,7 @@ static void eval_move(const MoveProblem& P, const int32_t* lab, int alpha, MoveW
     size_t arcs = 0;
     for (int i : cand) arcs += (size_t)(g.off[i + 1] - g.off[i]);
     auto run_network = [&](auto& mf) {
+      GC_TICK(t_build);
       mf.reset((int)cand.size(), 2 * arcs + 2 * cand.size());
       src.assign(cand.size(), 0);
       snk.assign(cand.size(), 0);
@@ -450,7 +491,10 @@ static void eval_move(const MoveProblem& P, const int32_t* lab, int alpha, MoveW
         src[a] = cost[(size_t)i * L + li] + (int64_t)potts * s_w;
       }
       for (size_t a = 0; a < cand.size(); ++a) mf.add_terminal((int)a, src[a], snk[a]);
+      GC_ACC(3, t_build);
+      GC_TICK(t_flow);
       mf.solve();
+      GC_ACC(4, t_flow);
       for (size_t a = 0; a < cand.size(); ++a) {
         const bool sw = !mf.sink_side((int)a);
         trial[cand[a]] = sw ? alpha : lab[cand[a]];
@@ -461,6 +505,7 @@ static void eval_move(const MoveProblem& P, const int32_t* lab, int alpha, MoveW
     if (solver == 2 || (solver == 0 && (int)cand.size() >= PR_MIN_NODES)) run_network(ws.mfpr);
     else run_network(ws.mf);
   }
+  GC_TICK(t_tally);
   if (any) {
     // energy of every term that involves a network site or a sure switcher, before and after (each pair once)
     int64_t before = 0, after = 0;
@@ -491,6 +536,7 @@ static void eval_move(const MoveProblem& P, const int32_t* lab, int alpha, MoveW
   }
   for (int i : cand) var[i] = -1;
   for (int i : fsw) swm[i] = 0;
+  GC_ACC(5, t_tally);
 }
 
 // ---------------------------------------------------------------------------
@@ -645,6 +691,7 @@ static uint64_t csr_key(int N, const int64_t* offsets, const int32_t* adj) {
 mh_status alpha_expansion(const int32_t* cost, int N, int L, int potts, const int64_t* offsets, const int32_t* adj,
                           const int32_t* init, int max_cycles, int32_t* lab, int64_t* energy_out) {
   if (N <= 0 || L < 1) return MH_EINVAL;
+  GC_TICK(t_total);
   for (int i = 0; i < N; ++i) {
     lab[i] = init ? init[i] : 0;
     if (lab[i] < 0 || lab[i] >= L) return MH_EINVAL;
@@ -732,6 +779,7 @@ mh_status alpha_expansion(const int32_t* cost, int N, int L, int potts, const in
     return true;
   };
 
+  GC_ACC(7, t_total);
   if (max_cycles < 0) max_cycles = 1 << 30;
   const int64_t max_moves = (int64_t)std::min<int64_t>(max_cycles, (1LL << 40) / L) * L;
   int idle_moves = 0;   // consecutive moves that changed nothing: L of them = a full sweep over an unchanged labelling
@@ -756,9 +804,13 @@ mh_status alpha_expansion(const int32_t* cost, int N, int L, int potts, const in
     for (int j = 0; j < nw && !stop; ++j, ++move) {
       const int alpha = (a0 + j) % L;
       ++idle_moves;
-      if (!known_idle(alpha)) {
+      GC_TICK(t_memo);
+      const bool idle_known = known_idle(alpha);
+      GC_ACC(6, t_memo);
+      if (!idle_known) {
         const bool usable = pool && nw > 1 && speculated[j] && clean_since(alpha, res[j].touched, res[j].any_c0, snapshot);
         if (!usable) eval_move(P, lab, alpha, ws[0], res[j], true);
+        GC_TICK(t_commit);
         if (!res[j].sw.empty()) {
           for (int i : res[j].sw) { lab[i] = alpha; cur[i] = cost[(size_t)i * L + alpha]; log.push_back(i); }
           E_delta += res[j].delta;
@@ -767,6 +819,7 @@ mh_status alpha_expansion(const int32_t* cost, int N, int L, int potts, const in
         Memo& m = memo[alpha];
         m.valid = true; m.any_c0 = res[j].any_c0; m.pos = log.size();
         m.touched.swap(res[j].touched);
+        GC_ACC(9, t_commit);
       }
       if (alpha == L - 1) {   // end of a cycle: GCO stops when the cycle left the energy unchanged
         if (E_delta == 0) stop = true;
@@ -777,6 +830,7 @@ mh_status alpha_expansion(const int32_t* cost, int N, int L, int potts, const in
   }
   if (pool) pool->release();
   if (energy_out) *energy_out = total_energy(cost, N, L, potts, g, lab);
+  GC_ACC(8, t_total);
   return MH_OK;
 }
 
