@@ -53,6 +53,7 @@ struct GcProfPrinter {
     std::fprintf(stderr, "[gc profile] moves with candidates %llu: mean C0 %.1f, decided at once %.1f, network sites %.1f (non-empty networks %llu), sure switchers %.1f\n",
                  g_prof_n[1], g_prof[10] / (double)g_prof_n[1], g_prof[11] / (double)g_prof_n[1], g_prof[12] / (double)g_prof_n[1], g_prof_n[12],
                  g_prof[13] / (double)g_prof_n[1]);
+    std::fprintf(stderr, "[gc profile] accepted moves %llu, sites switched %llu\n", g_prof_n[14], g_prof[14]);
     for (int i = 0; i < 10; ++i)
       std::fprintf(stderr, "[gc profile] %-16s %10.1f Mcycles  (%llu)  %5.1f %%\n", names[i], g_prof[i] / 1e6, g_prof_n[i],
                    100.0 * g_prof[i] / (double)(g_prof[8] ? g_prof[8] : 1));
@@ -811,6 +812,9 @@ mh_status alpha_expansion(const int32_t* cost, int N, int L, int potts, const in
         const bool usable = pool && nw > 1 && speculated[j] && clean_since(alpha, res[j].touched, res[j].any_c0, snapshot);
         if (!usable) eval_move(P, lab, alpha, ws[0], res[j], true);
         GC_TICK(t_commit);
+#ifdef MH_GC_PROFILE
+        g_prof[14] += res[j].sw.size(); g_prof_n[14] += !res[j].sw.empty();
+#endif
         if (!res[j].sw.empty()) {
           for (int i : res[j].sw) { lab[i] = alpha; cur[i] = cost[(size_t)i * L + alpha]; log.push_back(i); }
           E_delta += res[j].delta;
