@@ -500,8 +500,9 @@ def main():
                       "algorithmic": f"4 B/residual x {nd} x {kd + 1} per launch (the array GCO's setDataCost(int*) indexes)",
                       "kernel_ms": ms32,
                       "int16": {"achieved": gbs16, "frac": gbs16 / hbm_peak, "kernel_ms": ms16,
-                                "note": "2 B/residual: HBM outruns the arithmetic (and the store warp, which completes "
-                                        "up to 15 elements per row for whole-sector writes); not HBM-bound"}}
+                                "note": "2 B/residual: bound by the kernel's FP32 arithmetic, not by HBM (with the row heads on the "
+                                        "compute warps int16 and int32 launches take the same time); 0.70 of HBM would need "
+                                        "2.3e12 residuals/s, more than the fused argmin kernel reaches"}}
 
     # ---- CPU baseline: the reference's own dataEnergy on a bounded sample ---------------------------------------------------------
     cpu = None

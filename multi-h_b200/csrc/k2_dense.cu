@@ -102,7 +102,15 @@ __device__ __forceinline__ u64 add2(u64 a, u64 b) {
 
 // CONV: 1 = FMUL2.RM by 2^-149 (bit pattern of the denormal = the integer), 2 = FADD2.RM of 2^23 (low mantissa bits = the
 // integer), 3 = F2I.FLOOR
-template <typename OutT, int CONV>
+// HEADS_BY_COMPUTE: the elements in front of the rows (see above) are computed by the compute warps — warp w takes tile row w, its
+// lanes j < phase(w) one element each, hypotheses parked in shared memory — and the store warp only issues copies.  Why: the
+// store warp is ONE warp among the ~7 resident on its scheduler; with the heads (4 passes of scalar residuals for int16, 2 for
+// int32) its ~250 instructions per tile at a seventh of the issue rate were the tile period of the whole CTA (measured: 3400
+// cycles per tile for int16, 2660 for int32, the compute warps waiting for a free stage in 52 % of all samples).  Measured A/B
+// (1M x 1025): int16 0.999 -> 0.846 ms; int32 0.789 -> 0.849 ms — with the heads on the compute warps both element sizes take
+// the same time, i.e. the kernel is then bound by its arithmetic, which for int32 is slower than its store-bound 0.789 ms.  So
+// the default is: compute-warp heads for int16, store-warp heads for int32.
+template <typename OutT, int CONV, bool HEADS_BY_COMPUTE = (sizeof(OutT) == 2)>
 __global__ void __launch_bounds__(DT_THREADS, 3)
 cost_dense_tiled_kernel(const float4* __restrict__ pts, long long N, const float* __restrict__ hyp, int K,
                         OutT* __restrict__ out, CostParams cp, int Kt, int nchunks, int g_full, int g_last) {
@@ -120,6 +128,7 @@ cost_dense_tiled_kernel(const float4* __restrict__ pts, long long N, const float
   const unsigned s_pts = s_stage + DT_STAGES * STAGEB;
   const unsigned s_full = s_pts + DT_STAGES * PTSB;
   const unsigned s_empty = s_full + DT_STAGES * 8;
+  const unsigned s_head = s_empty + DT_STAGES * 8;   // HEADS_BY_COMPUTE: [DT_P rows][SEC lanes][12 floats] head hypotheses
 
   const int tid = threadIdx.x;
   const long long L = (long long)K + 1;
@@ -181,10 +190,11 @@ cost_dense_tiled_kernel(const float4* __restrict__ pts, long long N, const float
     };
     if (lane == 0)
       for (int t = 0; t < DT_STAGES; ++t) fetch_pts(t);
-    // slot = (tile row, element j in front of the chunk's first column); slot s * 32 + lane is this lane's in pass s.  The
-    // element is matrix column c_lo - g + j of the same row, or — chunk 0 — column L - g + j of the row before.
     float hs[NPASS][9];
     int s_row[NPASS], s_act[NPASS];
+    if (!HEADS_BY_COMPUTE) {
+    // slot = (tile row, element j in front of the chunk's first column); slot s * 32 + lane is this lane's in pass s.  The
+    // element is matrix column c_lo - g + j of the same row, or — chunk 0 — column L - g + j of the row before.
 #pragma unroll
     for (int s = 0; s < NPASS; ++s) {
       const int slot = s * 32 + lane, rr = slot / SEC, j = slot % SEC;
@@ -201,6 +211,7 @@ cost_dense_tiled_kernel(const float4* __restrict__ pts, long long N, const float
         hs[s][7] = v.w; hs[s][8] = w.x;
       }
     }
+    }
     const int my_g = (int)phase(lane % DT_P);                  // lane r < DT_P issues row r's copy
     const int my_e = (my_g + ncols) & (SEC - 1);               // elements of the row's trailing partial sector
     const bool tail_region = last_chunk && Kt < K;             // columns after this chunk belong to the tail kernel
@@ -208,6 +219,7 @@ cost_dense_tiled_kernel(const float4* __restrict__ pts, long long N, const float
     for (long long pb = bx; pb < NB; pb += gdim, ++it) {
       const int b = it % DT_STAGES;
       const unsigned st = s_stage + b * STAGEB;
+      if (!HEADS_BY_COMPUTE) {
       // -- elements in front of the rows, while the compute warps are busy with the tile
       dt_mbar_wait(s_empty + 8 * b, (it / DT_STAGES) & 1);     // the correspondences have landed (and the stage is free)
       // (all loads, then the independent residual chains, then the stores: the passes overlap instead of queueing)
@@ -227,6 +239,7 @@ cost_dense_tiled_kernel(const float4* __restrict__ pts, long long N, const float
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncwarp();
+      }
       dt_mbar_wait(s_full + 8 * b, (it / DT_STAGES) & 1);   // every compute warp has staged (and proxy-fenced) its columns
       // -- lane r < DT_P: row r = staged elements [0, g + ncols), column c_lo at g; whole sectors go out as one bulk copy
       const long long p = pb * DT_P + lane;
@@ -295,6 +308,20 @@ cost_dense_tiled_kernel(const float4* __restrict__ pts, long long N, const float
   const u64 KS2 = pk(kslope, kslope), LAM2 = pk(cp.lam, cp.lam), HALF2 = pk(0.5f, 0.5f);
   const u64 DEN2 = pk(__int_as_float(1), __int_as_float(1));   // 2^-149
   const u64 MAG2 = pk(8388608.f, 8388608.f);                   // 2^23
+  // HEADS_BY_COMPUTE: warp w owns the elements in front of tile row w: lane j < phase(w) computes matrix column c_lo - g + j of
+  // the row (chunk 0: column L - g + j of the row before), with that column's hypothesis read back from shared memory
+  const int hw = tid >> 5, hj = tid & 31;
+  const int hg = (int)phase(hw);
+  const bool head_lane = HEADS_BY_COMPUTE && hj < hg;
+  const unsigned head_slot = s_head + (unsigned)((hw * SEC + (hj & (SEC - 1))) * 48);
+  if (head_lane) {
+    const long long col = (cy == 0 ? L : (long long)c_lo) - hg + hj;   // >= 1: the tiled kernel runs with K >= 128
+    const float4* hp = reinterpret_cast<const float4*>(hyp + (size_t)(col - 1) * 12);
+    const float4 u = __ldg(hp), v = __ldg(hp + 1), w = __ldg(hp + 2);
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" :: "r"(head_slot), "f"(u.x), "f"(u.y), "f"(u.z), "f"(u.w) : "memory");
+    asm volatile("st.shared.v4.f32 [%0+16], {%1, %2, %3, %4};" :: "r"(head_slot), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+    asm volatile("st.shared.v4.f32 [%0+32], {%1, %2, %3, %4};" :: "r"(head_slot), "f"(w.x), "f"(w.y), "f"(w.z), "f"(w.w) : "memory");
+  }
   // staging address of this thread's first hypothesis in the rows of stage 0
   unsigned sbase[DT_P];
 #pragma unroll
@@ -363,6 +390,17 @@ cost_dense_tiled_kernel(const float4* __restrict__ pts, long long N, const float
       quad(std::integral_constant<int, 4>{});
       static_assert(DT_P == 8, "row() calls above cover 8 rows");
     }
+    if (HEADS_BY_COMPUTE) {
+      const long long p = pb * DT_P + hw;
+      if (head_lane && p < N && (cy > 0 || p > 0)) {
+        const float4 u = dt_lds128<0>(head_slot), v = dt_lds128<16>(head_slot), w = dt_lds128<32>(head_slot);
+        const float h[9] = {u.x, u.y, u.z, u.w, v.x, v.y, v.z, v.w, w.x};
+        float4 q;
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(q.x), "=f"(q.y), "=f"(q.z), "=f"(q.w)
+                     : "r"(s_pts + b * PTSB + (hw + (cy > 0 ? 1 : 0)) * 16));
+        dt_sts<0>(s_stage + b * STAGEB + hw * ROWB + hj * SZ, cost_of(residual(h, q.x, q.y, q.z, q.w), cp), (OutT*)nullptr);
+      }
+    }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // staged costs -> visible to the TMA engine
     __syncwarp();
     if ((tid & 31) == 0) dt_mbar_arrive(s_full + 8 * b);
@@ -399,7 +437,8 @@ template <typename OutT, int CONV>
 static mh_status launch_tiled(mh_ctx* ctx, const float4* d_pts, int64_t N, const float* d_hyp, int K, OutT* d_cost,
                               const CostParams& cp) {
   constexpr int SEC = 32 / (int)sizeof(OutT);
-  const size_t smem = (size_t)DT_STAGES * DT_P * (DT_KC + SEC) * sizeof(OutT) + (size_t)DT_STAGES * (DT_P + 1) * 16 + 2 * DT_STAGES * 8;
+  const size_t smem = (size_t)DT_STAGES * DT_P * (DT_KC + SEC) * sizeof(OutT) + (size_t)DT_STAGES * (DT_P + 1) * 16 + 2 * DT_STAGES * 8 +
+                      (size_t)DT_P * SEC * 48;   // + the head hypotheses
   const long long L = (long long)K + 1;
   const long long NB = (N + DT_P - 1) / DT_P;
   const int rem = K % DT_KC;
