@@ -10,20 +10,21 @@
 // listed in SURVEY.md §8(a); every function cites the reference file:line it
 // follows (paths relative to /root/reference/MultiH/MultiH/).
 //
-// Parity status: the reference (MSVC + PPL + OpenCV 3.1.0) cannot be built or
-// run here, and it ships no unit tests or per-function golden vectors.  The
-// restatement is therefore pinned by (1) tests/golden/*.npz, produced by
-// tests/golden/make_golden.py — an independent line-by-line transliteration of
-// the same reference functions on top of the real OpenCV numerical routines
-// (cv2.eigen, cv2.invert(DECOMP_SVD), cv2 4.13; the reference pins 3.1.0), including numpy / Python-list
-// transliterations of MeanShiftClustering::Cluster (golden_meanshift.npz) and HomographyCompatibilityCheck
-// (golden_compat.npz) with the MSVC rand(),
-// (2) analytic known-answer tests (noise-free plane => generating H),
-// (3) the integer cost constants 4901 / 9802 / 0..200 at default parameters,
-// (4) the reference's own alpha-expansion compiled in place (oracle/_ref) and
-// (5) the coarse structure of Executable/results/barrsmith.  Per-point labels of
-// the shipped multih.exe are NOT reproducible => "parity
-// pinned on restated functions, unpinned on the end-to-end labelling".
+// Parity status: PINNED ON THE REFERENCE SOURCE.  oracle/Makefile compiles the reference's own MultiH.cpp,
+// MeanShiftClustering.h, Homography_RefineHAFCallback.h, Homography_Refine3PTCallback.h, the LMSolverImpl of Utilities.hpp and
+// GCO, unmodified and where they lie under /root/reference, against oracle/cvshim/mini_cv.hpp (a stand-in for the OpenCV 3.1
+// surface those files use) into oracle/_ref/libmultih_ref.so / libgco_ref.so (wrappers: ref_multih_wrapper.cpp,
+// gco_ref_wrapper.cpp; the reference's MSVC project / PPL build is not run).  tests/test_oracle.py checks this restatement
+// against that library function by function (GetHomographyHAF, GetHomography3PT + NormalizePoints, HomographyHAFNonminimal,
+// dataEnergy, smoothnessEnergy, MeanShiftClustering<double>::Cluster, the LM solver + 3PT callback) and as a whole
+// (MultiH::Process() on the bundled pair: same survivors, labels and homographies, with and without the LM polish).
+// Second, independent pins kept from round 1: (1) tests/golden/*.npz, produced by tests/golden/make_golden.py — line-by-line
+// transliterations of the same reference functions on the real OpenCV numerical routines (cv2.eigen, cv2.invert(DECOMP_SVD),
+// cv2.solvePoly; cv2 4.13, the reference pins 3.1.0), including numpy / Python-list transliterations of
+// MeanShiftClustering::Cluster (golden_meanshift.npz) and HomographyCompatibilityCheck (golden_compat.npz) with the MSVC rand(),
+// (2) analytic known-answer tests (noise-free plane => generating H), (3) the integer cost constants 4901 / 9802 / 0..200 at
+// default parameters.  What stays unpinned is only the output FILE of the shipped multih.exe (another build, OpenCV's RANSAC for
+// F, FLANN's randomised trees, unseeded rand(): SURVEY.md §4) — parity is against the reference source run on identical inputs.
 //
 // Third-party arithmetic restated here (absent from /root/reference): OpenCV
 // 3.1.0 cv::eigen on symmetric input (Jacobi; eigenvalues descending,
