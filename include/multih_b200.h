@@ -224,6 +224,15 @@ mh_status mh_neighbourhood(mh_ctx* ctx, const double* pts_host, int32_t N, doubl
 mh_status mh_alpha_expansion(mh_ctx* ctx, const int32_t* cost_host, int32_t N, int32_t L, int32_t potts,
                              const int64_t* offsets_host, const int32_t* adj_host, const int32_t* init_labels,
                              int32_t max_cycles, int32_t* labels_out, int64_t* energy_out);
+/* The same with sparse-with-default data costs (cf. GCO's setDataCost(SparseDataCost), GCoptimization.h:220-224): per site up to
+ * kmax entries (label << 16 | cost) for labels 1..L-1 and their number; label 0 (the outlier label of MultiH.cpp:488-489) costs
+ * cost_label0 at every site, a label that is not listed costs cost_default (MultiH.cpp:499-500: d2 >= T).  This is what
+ * mh_process feeds its labelling steps: N x kmax words leave the device instead of the N x (K + 1) matrix.  counts[i] > kmax is
+ * MH_EINVAL (truncated list).  Result identical to mh_alpha_expansion on the expanded matrix. */
+mh_status mh_alpha_expansion_sparse(mh_ctx* ctx, const uint32_t* lists_host /*[N][kmax]*/, const int32_t* counts_host /*[N]*/,
+                                    int32_t kmax, int32_t N, int32_t L, int32_t cost_label0, int32_t cost_default, int32_t potts,
+                                    const int64_t* offsets_host, const int32_t* adj_host, const int32_t* init_labels,
+                                    int32_t max_cycles, int32_t* labels_out, int64_t* energy_out);
 
 /* ---- whole path ------------------------------------------------------------
  * MultiH::Process (MultiH.cpp:42-98) from ComputeLocalHomographies on, with F supplied:

@@ -28,7 +28,7 @@ SYMBOLS = [
     "mh_inlier_stats", "mh_inliers_of_homography", "mh_features10", "mh_features6", "mh_set_rng_state", "mh_get_rng_state", "mh_meanshift", "mh_refit_haf",
     "mh_refit_haf_accumulate", "mh_refit_haf_solve", "mh_labels_from_best", "mh_pack_inlier_counts", "mh_refit_3pt", "mh_modes_to_hypotheses", "mh_neighbourhood", "mh_alpha_expansion", "mh_compatibility_check", "mh_compat_plan", "mh_compat_decide", "mh_process", "mh_get_energy",
     "mh_get_iterations", "mh_get_stage_ms", "mh_diag_fp32_peak", "mh_diag_mma_tf32_peak", "mh_diag_set_fused_variant", "mh_diag_set_fast_config", "mh_diag_get_fast_config", "mh_diag_set_dense_variant", "mh_diag_get_alternating_ms", "mh_diag_set_neighbourhood_backend",
-    "mh_comm_unique_id", "mh_comm_init", "mh_comm_destroy", "mh_comm_rank", "mh_comm_world", "mh_comm_broadcast",
+    "mh_alpha_expansion_sparse", "mh_comm_unique_id", "mh_comm_init", "mh_comm_destroy", "mh_comm_rank", "mh_comm_world", "mh_comm_broadcast",
     "mh_comm_allreduce_sum_f64", "mh_step_sharded", "mh_step_sharded_finish",
 ]
 
@@ -148,6 +148,26 @@ def alpha_expansion(cost, potts, offsets, adj, init=None, max_cycles=1000):
                                   C.byref(energy))
     if st:
         raise MHError(st, "mh_alpha_expansion")
+    return labels, int(energy.value)
+
+
+def alpha_expansion_sparse(lists, counts, L, cost_label0, cost_default, potts, offsets, adj, init=None, max_cycles=1000):
+    """mh_alpha_expansion_sparse: per-site (label << 16 | cost) lists + the two default costs instead of the dense matrix."""
+    lists = _np(lists, np.uint32)
+    N, kmax = lists.shape
+    counts = _np(counts, np.int32)
+    offsets = _np(offsets, np.int64)
+    adj = _np(adj, np.int32)
+    if adj.size == 0:
+        adj = np.zeros(1, dtype=np.int32)
+    init_a = None if init is None else _np(init, np.int32)
+    labels = np.zeros(N, dtype=np.int32)
+    energy = C.c_int64(0)
+    st = lib().mh_alpha_expansion_sparse(None, _p(lists, C.c_uint32), _p(counts, C.c_int32), int(kmax), N, int(L), int(cost_label0),
+                                         int(cost_default), int(potts), _p(offsets, C.c_int64), _p(adj, C.c_int32),
+                                         _p(init_a, C.c_int32), int(max_cycles), _p(labels, C.c_int32), C.byref(energy))
+    if st:
+        raise MHError(st, "mh_alpha_expansion_sparse")
     return labels, int(energy.value)
 
 

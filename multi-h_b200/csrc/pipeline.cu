@@ -83,6 +83,34 @@ mh_status mh_alpha_expansion(mh_ctx* ctx, const int32_t* cost, int32_t N, int32_
   return st;
 }
 
+// Sparse-with-default form of the same call (cf. GCO's setDataCost(SparseDataCost), GCoptimization.h:220-224): per site up to
+// kmax entries (label << 16 | cost), label 1..L-1, as cost_list64_kernel / the pipeline's labelling step produce them; label 0
+// (the outlier label) costs cost_label0 everywhere and every label not listed costs cost_default.  A site with more than kmax
+// entries (count > kmax) is an error: the lists would be truncated.  The solver indexes a dense matrix, which is built here (in the
+// caller-provided or a thread-local buffer), so the result is exactly mh_alpha_expansion's on the expanded costs.
+mh_status mh_alpha_expansion_sparse(mh_ctx* ctx, const uint32_t* lists, const int32_t* counts, int32_t kmax, int32_t N, int32_t L,
+                                    int32_t cost_label0, int32_t cost_default, int32_t potts, const int64_t* offsets,
+                                    const int32_t* adj, const int32_t* init, int32_t max_cycles, int32_t* labels, int64_t* energy) {
+  if (!lists || !counts || !labels || N <= 0 || L < 1 || kmax < 1)
+    return ctx ? fail(ctx, MH_EINVAL, "mh_alpha_expansion_sparse: bad arguments") : MH_EINVAL;
+  static thread_local std::vector<int32_t> dense;
+  dense.resize((size_t)N * L);
+  for (int i = 0; i < N; ++i) {
+    if (counts[i] < 0 || counts[i] > kmax)
+      return ctx ? fail(ctx, MH_EINVAL, "mh_alpha_expansion_sparse: a site has more entries than kmax") : MH_EINVAL;
+    int32_t* row = dense.data() + (size_t)i * L;
+    row[0] = cost_label0;
+    std::fill(row + 1, row + L, cost_default);
+    const uint32_t* e = lists + (size_t)i * kmax;
+    for (int k = 0; k < counts[i]; ++k) {
+      const uint32_t l = e[k] >> 16;
+      if (l == 0 || l >= (uint32_t)L) return ctx ? fail(ctx, MH_EINVAL, "mh_alpha_expansion_sparse: label out of range") : MH_EINVAL;
+      row[l] = (int32_t)(e[k] & 0xffffu);
+    }
+  }
+  return mh_alpha_expansion(ctx, dense.data(), N, L, potts, offsets, adj, init, max_cycles, labels, energy);
+}
+
 // HomographyCompatibilityCheck (MultiH.cpp:100-222) in three parts.
 //   mh_compat_plan   (host)  the sampling: rand() draws without replacement from a point vector whose order evolves from trial
 //                            to trial (:142-154, :183-194) — sequential index bookkeeping, replayed exactly;
@@ -438,11 +466,10 @@ mh_status mh_process(mh_ctx* ctx, const double* pts, const double* aff, const do
     const int L = K + 1;
     tm = now_ms();
     MH_TRY(upload_hyps(K));
-    cost.resize((size_t)N * L);
     // The labelling step's data costs (dataEnergy, MultiH.cpp:473-504).  Precise path: sparse with default — the device lists
     // the few (label, cost) entries with d2 < T per site (cost_list64_kernel), every other entry is one of two constants, so
-    // N x kmax words cross the bus instead of the N x (K + 1) matrix; the host solver indexes a dense matrix, which is filled
-    // here.  A site with more than kmax entries in range (rare) makes this step fall back to the dense matrix.
+    // N x kmax words cross the bus instead of the N x (K + 1) matrix and go to the solver as they are
+    // (mh_alpha_expansion_sparse).  A site with more than kmax entries in range (rare) makes this step fall back to the dense matrix.
     const int kmax = 32;
     const double lam_d = 100.0 / P.lambda, T_d = P.thr_homography * P.thr_homography * 81.0 / 16.0;
     const int c_out = (int)std::round(lam_d * T_d), c_far = 2 * c_out;
@@ -456,17 +483,9 @@ mh_status mh_process(mh_ctx* ctx, const double* pts, const double* aff, const do
       MH_TRY(mh_memcpy_d2h(ctx, sparse.data(), b_cost.p, sizeof(uint32_t) * sparse.size()));
       const uint32_t* cnt = sparse.data() + (size_t)N * kmax;
       for (int i = 0; i < N && sparse_ok; ++i) sparse_ok = cnt[i] <= (uint32_t)kmax;
-      if (sparse_ok) {
-        for (int i = 0; i < N; ++i) {
-          int32_t* row = cost.data() + (size_t)i * L;
-          row[0] = c_out;
-          std::fill(row + 1, row + L, c_far);
-          const uint32_t* e = sparse.data() + (size_t)i * kmax;
-          for (uint32_t k = 0; k < cnt[i]; ++k) row[e[k] >> 16] = (int32_t)(e[k] & 0xffffu);
-        }
-      }
     }
     if (!sparse_ok) {
+      cost.resize((size_t)N * L);
       MH_TRY(b_cost.alloc(ctx, sizeof(int32_t) * (uint64_t)N * L));
       if (precise) MH_TRY(launch_cost_dense64(ctx, pts64, N, b_hyp64.as<double>(), K, b_cost.as<int32_t>()));
       else MH_TRY(mh_data_cost_dense(ctx, b_pts.p, N, b_hyp.p, K, b_cost.p, 4));
@@ -480,8 +499,13 @@ mh_status mh_process(mh_ctx* ctx, const double* pts, const double* aff, const do
     int64_t e64 = 0;
     ctx->alt_ms[2] += now_ms() - tm;
     tm = now_ms();
-    MH_TRY(mh_alpha_expansion(ctx, cost.data(), N, L, potts, offsets.data(), adj.data(), init_ptr, P.max_gc_cycles,
-                              gc_labels.data(), &e64));
+    if (sparse_ok)   // the lists go to the solver as they came off the device: sparse with the two default costs
+      MH_TRY(mh_alpha_expansion_sparse(ctx, sparse.data(), reinterpret_cast<const int32_t*>(sparse.data() + (size_t)N * kmax), kmax, N,
+                                       L, c_out, c_far, potts, offsets.data(), adj.data(), init_ptr, P.max_gc_cycles,
+                                       gc_labels.data(), &e64));
+    else
+      MH_TRY(mh_alpha_expansion(ctx, cost.data(), N, L, potts, offsets.data(), adj.data(), init_ptr, P.max_gc_cycles,
+                                gc_labels.data(), &e64));
     ctx->alt_ms[3] += now_ms() - tm;
     tm = now_ms();
     const double energy = (double)e64;

@@ -268,3 +268,31 @@ def test_compatibility_check_host_halves_replay_the_oracle(mh, orc):
         assert rem_o[len(sc.planes)] and not rem_o[:len(sc.planes)].any()   # the garbage cluster goes, the planes stay
         # the 7-member outlier cluster: removed untested when below min_inliers, tested (n >= 4, even-length median) and removed otherwise
         assert rem_o[len(sc.planes) + 1] and np.isnan(med_o[len(sc.planes) + 1]) == (min_inl > 7)
+
+
+def test_alpha_expansion_sparse_with_default_equals_dense(mh, orc):
+    """mh_alpha_expansion_sparse (per-site (label << 16 | cost) lists + the two default costs, what mh_process's labelling step
+    ships from the device) = mh_alpha_expansion on the expanded dense matrix; a truncated list is refused."""
+    sc = mh.scenes.make_scene(1500, 5, seed=23)
+    H = np.concatenate([sc.planes, orc.haf_hypotheses(sc.pts[:40], sc.aff[:40], sc.F)])
+    cost = orc.data_cost_dense(sc.pts, H)                              # [N][K + 1], column 0 = outlier label
+    N, L = cost.shape
+    c_out, c_far = int(cost[0, 0]), int(cost.max())
+    assert (cost[:, 0] == c_out).all() and c_far == 2 * c_out
+    inr = cost[:, 1:] != c_far
+    kmax = int(inr.sum(1).max())
+    lists = np.zeros((N, kmax), dtype=np.uint32); counts = inr.sum(1).astype(np.int32)
+    for i in range(N):
+        ls = np.nonzero(inr[i])[0] + 1
+        lists[i, :len(ls)] = (ls.astype(np.uint32) << 16) | cost[i, ls].astype(np.uint32)
+    off, adj = mh.capi.neighbourhood(sc.pts, 200.0, 31)
+    l_d, e_d = mh.capi.alpha_expansion(cost, 50, off, adj)
+    l_s, e_s = mh.capi.alpha_expansion_sparse(lists, counts, L, c_out, c_far, 50, off, adj)
+    assert e_s == e_d and np.array_equal(l_s, l_d)
+    init = np.roll(l_d, 7)
+    l_d2, e_d2 = mh.capi.alpha_expansion(cost, 50, off, adj, init)
+    l_s2, e_s2 = mh.capi.alpha_expansion_sparse(lists, counts, L, c_out, c_far, 50, off, adj, init)
+    assert e_s2 == e_d2 and np.array_equal(l_s2, l_d2)
+    bad = counts.copy(); bad[3] = kmax + 1
+    with pytest.raises(mh.MHError):
+        mh.capi.alpha_expansion_sparse(lists, bad, L, c_out, c_far, 50, off, adj)
