@@ -37,7 +37,8 @@
 #include "../../include/multih_b200.h"
 #ifdef MH_GC_PROFILE
 #include <x86intrin.h>
-
+#endif
+#if defined(MH_GC_PROFILE) || defined(MH_GC_CHECK_TALLY)
 #include <cstdio>
 #endif
 
@@ -74,6 +75,7 @@ class MaxFlow {
  public:
   void reset(int n_nodes, size_t arc_hint) {
     n_ = n_nodes + 2; s_ = n_nodes; t_ = n_nodes + 1;
+    flow_ = 0;
     head_.assign(n_, -1);
     arc_.clear();
     arc_.reserve(arc_hint);
@@ -110,6 +112,7 @@ class MaxFlow {
           int64_t f = INT64_MAX;
           for (int e : path) f = std::min(f, arc[e].cap);
           for (int e : path) { arc[e].cap -= f; arc[e ^ 1].cap += f; }
+          flow_ += f;
           // restart from the first saturated arc
           size_t k = 0;
           while (k < path.size() && arc[path[k]].cap > 0) ++k;
@@ -143,9 +146,11 @@ class MaxFlow {
     }
   }
   bool sink_side(int x) const { return reach_t_[x] != 0; }
+  int64_t flow_value() const { return flow_; }   // value of the maximum flow (over the terminal-capacity differences)
 
  private:
   struct Arc { int64_t cap; int to, next; };
+  int64_t flow_ = 0;
   int n_ = 0, s_ = 0, t_ = 0;
   std::vector<int> head_, level_, it_, queue_, path_;
   std::vector<Arc> arc_;
@@ -163,6 +168,7 @@ class MaxFlowPR {
  public:
   void reset(int n_nodes, size_t arc_hint) {
     n_ = n_nodes;
+    flow_ = 0;
     first_.assign((size_t)n_, -1);
     excess_.assign((size_t)n_, 0);
     tcap_.assign((size_t)n_, 0);
@@ -179,6 +185,7 @@ class MaxFlowPR {
     else tcap_[x] = to_sink - from_source;
   }
   bool sink_side(int x) const { return d_[x] < dead_; }
+  int64_t flow_value() const { return flow_; }   // what reached the sink: the value of a maximum preflow = of a maximum flow
 
   void solve() {
     dead_ = n_ + 1;
@@ -202,6 +209,7 @@ class MaxFlowPR {
         if (tcap_[i] > 0 && d_[i] == 1) {
           const int64_t f = std::min(excess_[i], tcap_[i]);
           tcap_[i] -= f; excess_[i] -= f;
+          flow_ += f;
           continue;
         }
         int e = cur_[i];
@@ -266,6 +274,7 @@ class MaxFlowPR {
       if (excess_[i] > 0 && d_[i] < dead_) { inq_[i] = 1; queue_.push_back(i); }
     }
   }
+  int64_t flow_ = 0;
   int n_ = 0, dead_ = 1;
   std::vector<int> first_, d_, cur_, count_, queue_, bfs_;
   std::vector<char> inq_;
@@ -463,6 +472,9 @@ static void eval_move(const MoveProblem& P, const int32_t* lab, int alpha, MoveW
   for (size_t a = 0; a < cand.size(); ++a) var[cand[a]] = (int)a;
   std::vector<int32_t>& trial = ws.trial;
   bool any = !fsw.empty();
+  // energy of the network's optimum minus the energy with every network site keeping its label (both with the sure switchers
+  // switched): the network represents the energy exactly up to a constant, so this is (flow + SUM min(src, snk)) - SUM src
+  int64_t delta_net = 0;
   if (!cand.empty()) {
     size_t arcs = 0;
     for (int i : cand) arcs += (size_t)(g.off[i + 1] - g.off[i]);
@@ -491,11 +503,17 @@ static void eval_move(const MoveProblem& P, const int32_t* lab, int alpha, MoveW
         snk[a] = cost[(size_t)i * L + alpha] + (int64_t)potts * t_w;
         src[a] = cost[(size_t)i * L + li] + (int64_t)potts * s_w;
       }
-      for (size_t a = 0; a < cand.size(); ++a) mf.add_terminal((int)a, src[a], snk[a]);
+      int64_t sum_src = 0, sum_min = 0;
+      for (size_t a = 0; a < cand.size(); ++a) {
+        mf.add_terminal((int)a, src[a], snk[a]);
+        sum_src += src[a];
+        sum_min += std::min(src[a], snk[a]);
+      }
       GC_ACC(3, t_build);
       GC_TICK(t_flow);
       mf.solve();
       GC_ACC(4, t_flow);
+      delta_net = mf.flow_value() + sum_min - sum_src;
       for (size_t a = 0; a < cand.size(); ++a) {
         const bool sw = !mf.sink_side((int)a);
         trial[cand[a]] = sw ? alpha : lab[cand[a]];
@@ -508,28 +526,52 @@ static void eval_move(const MoveProblem& P, const int32_t* lab, int alpha, MoveW
   }
   GC_TICK(t_tally);
   if (any) {
-    // energy of every term that involves a network site or a sure switcher, before and after (each pair once)
+    // Energy change of the move = delta_net (above) + the change from switching the sure switchers alone, network sites keeping:
+    // every term that involves a sure switcher, before and after (each pair among them once).  GCO accepts a move only if it
+    // strictly lowers the energy.
     int64_t before = 0, after = 0;
-    auto tally = [&](int i, int ti) {
+    for (int i : fsw) {
       const int li = lab[i];
       before += cost[(size_t)i * L + li];
-      after += cost[(size_t)i * L + ti];
+      after += cost[(size_t)i * L + alpha];
       int32_t cb = 0, ca = 0;
       for (int64_t k = g.off[i]; k < g.off[i + 1]; ++k) {
-        const int j = g.nbr[k], vj = var[j], lj = lab[j];
-        const int inU = (vj >= 0) | swm[j];
-        const int tj = swm[j] ? alpha : (vj >= 0 ? trial[j] : lj);
-        const int once = (inU ^ 1) | (j < i);
+        const int j = g.nbr[k], lj = lab[j];
+        const int sj = swm[j];
+        const int once = (sj ^ 1) | (j < i);
         cb += g.w[k] * (once & (li != lj));
-        ca += g.w[k] * (once & (ti != tj));
+        ca += g.w[k] * (once & ((sj | (lj == alpha)) ^ 1));   // i is alpha afterwards: the pair costs w unless j is (or becomes) alpha
       }
       before += (int64_t)potts * cb;
       after += (int64_t)potts * ca;
-    };
-    for (int i : cand) tally(i, trial[i]);
-    for (int i : fsw) tally(i, alpha);
-    if (after < before) {   // GCO accepts a move only if it strictly lowers the energy
-      r.delta = after - before;
+    }
+    const int64_t delta = delta_net + (after - before);
+#ifdef MH_GC_CHECK_TALLY   // the direct tally over every network site and sure switcher (the previous implementation)
+    {
+      int64_t b2 = 0, a2 = 0;
+      auto tally = [&](int i, int ti) {
+        const int li = lab[i];
+        b2 += cost[(size_t)i * L + li];
+        a2 += cost[(size_t)i * L + ti];
+        int32_t cb = 0, ca = 0;
+        for (int64_t k = g.off[i]; k < g.off[i + 1]; ++k) {
+          const int j = g.nbr[k], vj = var[j], lj = lab[j];
+          const int inU = (vj >= 0) | swm[j];
+          const int tj = swm[j] ? alpha : (vj >= 0 ? trial[j] : lj);
+          const int once = (inU ^ 1) | (j < i);
+          cb += g.w[k] * (once & (li != lj));
+          ca += g.w[k] * (once & (ti != tj));
+        }
+        b2 += (int64_t)potts * cb;
+        a2 += (int64_t)potts * ca;
+      };
+      for (int i : cand) tally(i, trial[i]);
+      for (int i : fsw) tally(i, alpha);
+      if (a2 - b2 != delta) { std::fprintf(stderr, "[gc check] delta %lld vs tally %lld\n", (long long)delta, (long long)(a2 - b2)); std::abort(); }
+    }
+#endif
+    if (delta < 0) {
+      r.delta = delta;
       for (int i : fsw) r.sw.push_back(i);
       for (int i : cand)
         if (trial[i] == alpha) r.sw.push_back(i);
